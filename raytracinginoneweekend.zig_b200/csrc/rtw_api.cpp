@@ -1,0 +1,765 @@
+// rtw_api.cpp — implementation of the C ABI of include/rtw_cuda.h.
+//
+// Host side of the seam cut around the reference's render loop (src/main.zig:382-402): validates and
+// copies the flattened scene, lowers it to the fp32 device layout of rtw_device.cuh (this is where
+// f64 -> fp32 happens), builds the BVH, owns the device buffers, launches the kernels.  No CPU
+// fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rtw_cuda.h"
+#include "rtw_bvh.h"
+#include "rtw_kernels.h"
+
+using namespace rtw;
+
+namespace {
+
+// Spheres at least this large get the reference-point form of |o-c|^2 - r^2 (rtw_trace.cuh).
+constexpr double kBigSphereRadius = 64.0;
+// Scenes up to this many primitives default to the warp-uniform flat scan (measured crossover).
+constexpr uint32_t kFlatAutoMax = 64;
+constexpr uint32_t kFlatHardMax = 6144;  // 192 KB of shared memory
+
+thread_local std::string g_create_error;
+
+float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t upload(const std::vector<T> &h) {
+        release();
+        n = h.size();
+        if (n == 0) {  // keep a valid pointer so kernels never see null tables
+            return cudaMalloc(&p, sizeof(T));
+        }
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        return cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct rtw_ctx {
+    int device = 0;
+    int n_sms = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {};
+    bool have_scene = false;
+
+    DevBuf<DevPrim> prims_flat, prims_bvh;
+    DevBuf<uint32_t> bvh_prim_id, prim_material;
+    DevBuf<BvhNode> nodes;
+    DevBuf<DevXform> xforms;
+    DevBuf<DevBigSphere> bigs;
+    DevBuf<DevMaterial> materials;
+    DevBuf<DevTexture> textures;
+    DevBuf<DevImage> images;
+    DevBuf<DevPerlin> perlins;
+    DevBuf<RawPrim> raw_prims;
+    DevBuf<RawXform> raw_chains;
+    std::vector<cudaArray_t> image_arrays;
+    std::vector<cudaTextureObject_t> image_tex;
+    DevScene scene{};
+    RawScene raw{};
+    uint32_t n_prims = 0;
+    bool root_is_leaf = false;
+
+    DevBuf<float4> accum;       // internal accumulation buffer of rtw_cuda_render
+    DevBuf<uint8_t> rgb8;
+    DevBuf<unsigned int> tile_counter;
+    DevBuf<unsigned long long> stat_counters;
+    rtw_stats stats{};
+};
+
+namespace {
+
+int fail(rtw_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(ctx, 2, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+void free_images(rtw_ctx *c) {
+    for (auto t : c->image_tex) cudaDestroyTextureObject(t);
+    for (auto a : c->image_arrays) cudaFreeArray(a);
+    c->image_tex.clear();
+    c->image_arrays.clear();
+}
+
+// ---- leaf boxes: the reference's boudingBox rules -------------------------------------------------
+// sphere c +- r (hittable.zig:133-143); moving sphere = union of the boxes at time0 and time1
+// (hittable.zig:203-217); rects padded +-1e-4 on the thin axis (hittable.zig:305-316, 358-369,
+// 411-422); RotateY = box of the 8 rotated corners (hittable.zig:516-556); Translate shifts
+// (hittable.zig:491-498).
+Box3d leaf_box(const rtw_scene_desc *s, const rtw_prim &p) {
+    Box3d b{};
+    auto set = [&](double x0, double y0, double z0, double x1, double y1, double z1) {
+        b.mn[0] = x0; b.mn[1] = y0; b.mn[2] = z0; b.mx[0] = x1; b.mx[1] = y1; b.mx[2] = z1;
+    };
+    switch (p.kind) {
+        case RTW_PRIM_SPHERE:
+            set(p.v[0] - p.v[3], p.v[1] - p.v[3], p.v[2] - p.v[3], p.v[0] + p.v[3], p.v[1] + p.v[3], p.v[2] + p.v[3]);
+            break;
+        case RTW_PRIM_MOVING_SPHERE: {
+            const double r = p.v[8];
+            for (int a = 0; a < 3; ++a) {
+                const double c0 = p.v[a], c1 = p.v[3 + a];
+                const double o0 = c0 + (c1 - c0) * ((s->time0 - p.v[6]) / (p.v[7] - p.v[6]));
+                const double o1 = c0 + (c1 - c0) * ((s->time1 - p.v[6]) / (p.v[7] - p.v[6]));
+                b.mn[a] = std::fmin(o0 - r, o1 - r);
+                b.mx[a] = std::fmax(o0 + r, o1 + r);
+            }
+            break;
+        }
+        case RTW_PRIM_XY_RECT: set(p.v[0], p.v[2], p.v[4] - 0.0001, p.v[1], p.v[3], p.v[4] + 0.0001); break;
+        case RTW_PRIM_XZ_RECT: set(p.v[0], p.v[4] - 0.0001, p.v[2], p.v[1], p.v[4] + 0.0001, p.v[3]); break;
+        default: set(p.v[4] - 0.0001, p.v[0], p.v[2], p.v[4] + 0.0001, p.v[1], p.v[3]); break;
+    }
+    for (int x = p.xform; x >= 0; x = s->xforms[x].outer) {  // innermost -> outermost
+        const rtw_xform &xf = s->xforms[x];
+        if (xf.kind == RTW_XFORM_TRANSLATE) {
+            for (int a = 0; a < 3; ++a) { b.mn[a] += xf.v[a]; b.mx[a] += xf.v[a]; }
+        } else {
+            const double sn = xf.v[0], cs = xf.v[1];
+            Box3d o{};
+            for (int a = 0; a < 3; ++a) { o.mn[a] = INFINITY; o.mx[a] = -INFINITY; }
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j)
+                    for (int k = 0; k < 2; ++k) {
+                        const double x0 = i ? b.mx[0] : b.mn[0], y0 = j ? b.mx[1] : b.mn[1], z0 = k ? b.mx[2] : b.mn[2];
+                        const double q[3] = {cs * x0 + sn * z0, y0, -sn * x0 + cs * z0};
+                        for (int a = 0; a < 3; ++a) { o.mn[a] = std::fmin(o.mn[a], q[a]); o.mx[a] = std::fmax(o.mx[a], q[a]); }
+                    }
+            b = o;
+        }
+    }
+    return b;
+}
+
+// Compose an instance chain (innermost index `x`) into object = A*world + t, A = Ry.
+DevXform compose_chain(const rtw_scene_desc *s, int x) {
+    // collect outermost-first
+    std::vector<int> chain;
+    for (int k = x; k >= 0; k = s->xforms[k].outer) chain.push_back(k);
+    std::reverse(chain.begin(), chain.end());
+    double c = 1.0, sn = 0.0, t[3] = {0, 0, 0};  // p_obj = A p + t
+    for (int k : chain) {
+        const rtw_xform &xf = s->xforms[k];
+        if (xf.kind == RTW_XFORM_TRANSLATE) {  // p <- p - offset
+            for (int a = 0; a < 3; ++a) t[a] -= xf.v[a];
+        } else {  // p <- R p with R: x' = c x - s z, z' = s x + c z   (hittable.zig:563-564)
+            const double s2 = xf.v[0], c2 = xf.v[1];
+            const double nc = c2 * c - s2 * sn, ns = s2 * c + c2 * sn;
+            const double tx = c2 * t[0] - s2 * t[2], tz = s2 * t[0] + c2 * t[2];
+            c = nc; sn = ns; t[0] = tx; t[2] = tz;
+        }
+    }
+    DevXform d{};
+    d.c = (float)c; d.s = (float)sn; d.tx = (float)t[0]; d.ty = (float)t[1]; d.tz = (float)t[2];
+    return d;
+}
+
+int validate(rtw_ctx *ctx, const rtw_scene_desc *s) {
+    if (!s) return fail(ctx, 1, "scene is null");
+    if (s->n_prims && !s->prims) return fail(ctx, 1, "prims is null");
+    if (!(s->time1 >= s->time0)) return fail(ctx, 1, "time1 < time0");
+    for (uint32_t i = 0; i < s->n_xforms; ++i) {
+        const rtw_xform &x = s->xforms[i];
+        if (x.kind > RTW_XFORM_ROTATE_Y) return fail(ctx, 1, "xform %u: bad kind %u", i, x.kind);
+        if (x.outer < -1 || x.outer >= (int)s->n_xforms || x.outer == (int)i)
+            return fail(ctx, 1, "xform %u: bad outer index %d", i, x.outer);
+    }
+    for (uint32_t i = 0; i < s->n_xforms; ++i) {  // chains must terminate
+        uint32_t steps = 0;
+        for (int k = (int)i; k >= 0; k = s->xforms[k].outer)
+            if (++steps > s->n_xforms) return fail(ctx, 1, "xform %u: cyclic chain", i);
+    }
+    for (uint32_t i = 0; i < s->n_prims; ++i) {
+        const rtw_prim &p = s->prims[i];
+        if (p.kind > RTW_PRIM_YZ_RECT) return fail(ctx, 1, "prim %u: bad kind %u", i, p.kind);
+        if (p.material >= s->n_materials) return fail(ctx, 1, "prim %u: material %u out of range", i, p.material);
+        if (p.xform < -1 || p.xform >= (int)s->n_xforms) return fail(ctx, 1, "prim %u: xform %d out of range", i, p.xform);
+        if (p.kind == RTW_PRIM_MOVING_SPHERE && p.v[7] == p.v[6]) return fail(ctx, 1, "prim %u: time1 == time0", i);
+        if ((p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE) && p.xform >= 0)
+            return fail(ctx, 1, "prim %u: instanced spheres are not supported", i);
+    }
+    for (uint32_t i = 0; i < s->n_materials; ++i) {
+        const rtw_material &m = s->materials[i];
+        if (m.kind > RTW_MAT_DIFFUSE_LIGHT) return fail(ctx, 1, "material %u: bad kind %u", i, m.kind);
+        if ((m.kind == RTW_MAT_DIFFUSE || m.kind == RTW_MAT_DIFFUSE_LIGHT) && (m.texture < 0 || m.texture >= (int)s->n_textures))
+            return fail(ctx, 1, "material %u: texture %d out of range", i, m.texture);
+    }
+    for (uint32_t i = 0; i < s->n_textures; ++i) {
+        const rtw_texture &t = s->textures[i];
+        if (t.kind > RTW_TEX_IMAGE) return fail(ctx, 1, "texture %u: bad kind %u", i, t.kind);
+        if (t.kind == RTW_TEX_CHECKER && (t.a < 0 || t.b < 0 || t.a >= (int)s->n_textures || t.b >= (int)s->n_textures))
+            return fail(ctx, 1, "texture %u: checker child out of range", i);
+        if (t.kind == RTW_TEX_NOISE && (t.a < 0 || t.a >= (int)s->n_perlins)) return fail(ctx, 1, "texture %u: perlin out of range", i);
+        if (t.kind == RTW_TEX_IMAGE && (t.a < 0 || t.a >= (int)s->n_images)) return fail(ctx, 1, "texture %u: image out of range", i);
+    }
+    for (uint32_t i = 0; i < s->n_images; ++i)
+        if (!s->images[i].rgba8 || !s->images[i].width || !s->images[i].height) return fail(ctx, 1, "image %u: empty", i);
+    return 0;
+}
+
+DevCamera lower_camera(const rtw_camera *c) {
+    DevCamera d{};
+    d.ox = (float)c->origin[0]; d.oy = (float)c->origin[1]; d.oz = (float)c->origin[2];
+    d.hx = (float)c->horizontal[0]; d.hy = (float)c->horizontal[1]; d.hz = (float)c->horizontal[2];
+    d.vx = (float)c->vertical[0]; d.vy = (float)c->vertical[1]; d.vz = (float)c->vertical[2];
+    d.lx = (float)c->lower_left_corner[0]; d.ly = (float)c->lower_left_corner[1]; d.lz = (float)c->lower_left_corner[2];
+    d.ux = (float)c->u[0]; d.uy = (float)c->u[1]; d.uz = (float)c->u[2];
+    d.wx = (float)c->v[0]; d.wy = (float)c->v[1]; d.wz = (float)c->v[2];
+    d.lens_radius = (float)c->lens_radius; d.time0 = (float)c->time0; d.time1 = (float)c->time1;
+    return d;
+}
+
+int pick_variant(rtw_ctx *ctx, uint32_t requested, int *out) {
+    int v;
+    switch (requested) {
+        case RTW_VARIANT_AUTO: v = ctx->n_prims <= kFlatAutoMax ? VAR_FLAT : VAR_BVH; break;
+        case RTW_VARIANT_MEGA_FLAT: v = VAR_FLAT; break;
+        case RTW_VARIANT_MEGA_BVH: v = VAR_BVH; break;
+        case RTW_VARIANT_WAVEFRONT: return fail(ctx, 1, "variant WAVEFRONT is not built yet");
+        default: return fail(ctx, 1, "unknown variant %u", requested);
+    }
+    if (v == VAR_FLAT && ctx->n_prims > kFlatHardMax)
+        return fail(ctx, 1, "flat variant holds at most %u primitives in shared memory (scene has %u)", kFlatHardMax, ctx->n_prims);
+    *out = v;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t rtw_cuda_abi_version(void) { return RTW_ABI_VERSION; }
+
+const char *rtw_cuda_last_error(const rtw_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rtw_cuda_create(int device, rtw_ctx **out) {
+    rtw_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, 1, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, 3, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, 1, "device %d out of range (have %d)", device, count);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(nullptr, 3, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    ctx = new rtw_ctx();
+    ctx->device = device;
+    ctx->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "stream create failed"); }
+    for (auto &ev : ctx->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "event create failed"); }
+    if (ctx->tile_counter.alloc(1) != cudaSuccess || ctx->stat_counters.alloc(ST_COUNT) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, 2, "device allocation failed");
+    }
+    cudaMemset(ctx->stat_counters.p, 0, ST_COUNT * sizeof(unsigned long long));
+    *out = ctx;
+    return 0;
+}
+
+void rtw_cuda_destroy(rtw_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_images(ctx);
+    ctx->prims_flat.release(); ctx->prims_bvh.release(); ctx->bvh_prim_id.release(); ctx->prim_material.release();
+    ctx->nodes.release(); ctx->xforms.release(); ctx->bigs.release(); ctx->materials.release(); ctx->textures.release();
+    ctx->images.release(); ctx->perlins.release(); ctx->raw_prims.release(); ctx->raw_chains.release();
+    ctx->accum.release(); ctx->rgb8.release(); ctx->tile_counter.release(); ctx->stat_counters.release();
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (int rc = validate(ctx, s)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_scene = false;
+    const uint32_t n = s->n_prims;
+
+    // reference point for big spheres: centroid of the centres of everything that is not big
+    double cen[3] = {0, 0, 0};
+    uint32_t ncen = 0;
+    std::vector<Box3d> boxes(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        boxes[i] = leaf_box(s, s->prims[i]);
+        const rtw_prim &p = s->prims[i];
+        if (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius) continue;
+        for (int a = 0; a < 3; ++a) cen[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
+        ++ncen;
+    }
+    if (ncen) for (double &c : cen) c /= ncen;
+
+    // ---- lower to fp32 records --------------------------------------------------------------------
+    std::vector<DevPrim> flat(n);
+    std::vector<uint32_t> prim_mat(n);
+    std::vector<DevBigSphere> bigs;
+    std::vector<DevXform> xforms;
+    std::map<int, int> xform_slot;
+    std::vector<RawPrim> raw(n);
+    std::vector<RawXform> chains;
+    for (uint32_t i = 0; i < n; ++i) {
+        const rtw_prim &p = s->prims[i];
+        DevPrim d{};
+        prim_mat[i] = p.material;
+        uint32_t meta = 0;
+        if (p.kind == RTW_PRIM_SPHERE) {
+            d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
+            d.b = make_float4(0.f, 0.f, 0.f, 0.f);
+            meta = PK_SPHERE;
+            if (p.v[3] >= kBigSphereRadius && bigs.size() < 0xFFFFFEu) {
+                // q = point of the sphere surface nearest the scene's centre of interest
+                double dir[3] = {cen[0] - p.v[0], cen[1] - p.v[1], cen[2] - p.v[2]};
+                double len = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+                if (!(len > 0)) { dir[0] = 0; dir[1] = 1; dir[2] = 0; len = 1; }
+                // the device works from the fp32-rounded centre and q: keep the identities exact in f64
+                const double cf[3] = {(double)(float)p.v[0], (double)(float)p.v[1], (double)(float)p.v[2]};
+                const double rf = (double)(float)p.v[3];
+                DevBigSphere g{};
+                double q[3], m[3], mm = 0;
+                for (int a = 0; a < 3; ++a) q[a] = (double)(float)(cf[a] + dir[a] / len * rf);
+                for (int a = 0; a < 3; ++a) { m[a] = q[a] - cf[a]; }
+                g.qx = (float)q[0]; g.qy = (float)q[1]; g.qz = (float)q[2];
+                g.mx = (float)m[0]; g.my = (float)m[1]; g.mz = (float)m[2];
+                // K uses the fp32-rounded m so that |a + m|^2 - r^2 is what the kernel expands
+                for (int a = 0; a < 3; ++a) { const double mf = (double)(&g.mx)[a]; mm += mf * mf; }
+                g.K = (float)(mm - rf * rf);
+                bigs.push_back(g);
+                meta |= (uint32_t)bigs.size() << 8;
+            }
+        } else if (p.kind == RTW_PRIM_MOVING_SPHERE) {
+            // centre(time) = c0 + (c1-c0) (time-t0)/(t1-t0) = cb + vel*time   (hittable.zig:219-221)
+            const double inv = 1.0 / (p.v[7] - p.v[6]);
+            float vel[3], cb[3];
+            for (int a = 0; a < 3; ++a) {
+                const double v = (p.v[3 + a] - p.v[a]) * inv;
+                vel[a] = (float)v;
+                cb[a] = (float)(p.v[a] - v * p.v[6]);
+            }
+            d.a = make_float4(cb[0], cb[1], cb[2], (float)p.v[8]);
+            d.b = make_float4(vel[0], vel[1], vel[2], 0.f);
+            meta = PK_SPHERE;
+        } else {
+            d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
+            int slot = -1;
+            if (p.xform >= 0) {
+                auto it = xform_slot.find(p.xform);
+                if (it == xform_slot.end()) {
+                    xforms.push_back(compose_chain(s, p.xform));
+                    it = xform_slot.emplace(p.xform, (int)xforms.size() - 1).first;
+                }
+                slot = it->second;
+            }
+            d.b = make_float4((float)p.v[4], bits_to_float((uint32_t)slot), 0.f, 0.f);
+            meta = p.kind == RTW_PRIM_XY_RECT ? PK_XY : p.kind == RTW_PRIM_XZ_RECT ? PK_XZ : PK_YZ;
+        }
+        d.b.w = bits_to_float(meta);
+        flat[i] = d;
+
+        RawPrim &r = raw[i];
+        r.kind = p.kind; r.material = p.material;
+        std::memcpy(r.v, p.v, sizeof r.v);
+        r.chain_begin = (uint32_t)chains.size();
+        std::vector<RawXform> tmp;
+        for (int x = p.xform; x >= 0; x = s->xforms[x].outer) {
+            RawXform rx{};
+            rx.kind = s->xforms[x].kind;
+            rx.v[0] = s->xforms[x].v[0]; rx.v[1] = s->xforms[x].v[1]; rx.v[2] = s->xforms[x].v[2];
+            tmp.push_back(rx);
+        }
+        std::reverse(tmp.begin(), tmp.end());  // outermost first
+        r.chain_len = (uint32_t)tmp.size();
+        chains.insert(chains.end(), tmp.begin(), tmp.end());
+    }
+
+    // ---- BVH ------------------------------------------------------------------------------------------
+    BvhResult bvh = build_bvh(boxes, 4);
+    if (bvh.depth > (uint32_t)64) return fail(ctx, 2, "BVH depth %u exceeds the traversal stack", bvh.depth);
+    std::vector<DevPrim> leaf_order(n);
+    for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
+
+    // ---- materials / textures -------------------------------------------------------------------------
+    std::vector<DevMaterial> mats(s->n_materials);
+    for (uint32_t i = 0; i < s->n_materials; ++i) {
+        const rtw_material &m = s->materials[i];
+        mats[i] = DevMaterial{m.kind, m.texture, (float)m.albedo[0], (float)m.albedo[1], (float)m.albedo[2], (float)m.param, 0.f, 0.f};
+    }
+    std::vector<DevTexture> texs(s->n_textures);
+    for (uint32_t i = 0; i < s->n_textures; ++i) {
+        const rtw_texture &t = s->textures[i];
+        texs[i] = DevTexture{t.kind, t.a, t.b, (float)t.scale, (float)t.color[0], (float)t.color[1], (float)t.color[2], 0u};
+    }
+    std::vector<DevPerlin> perl(s->n_perlins);
+    for (uint32_t i = 0; i < s->n_perlins; ++i) {
+        const rtw_perlin &p = s->perlins[i];
+        if (!p.ranvec || !p.perm_x || !p.perm_y || !p.perm_z) return fail(ctx, 1, "perlin %u: null table", i);
+        for (int k = 0; k < 256; ++k) {
+            perl[i].ranvec[k] = make_float4((float)p.ranvec[3 * k], (float)p.ranvec[3 * k + 1], (float)p.ranvec[3 * k + 2], 0.f);
+            perl[i].perm[0][k] = (uint8_t)p.perm_x[k]; perl[i].perm[1][k] = (uint8_t)p.perm_y[k]; perl[i].perm[2][k] = (uint8_t)p.perm_z[k];
+        }
+    }
+    free_images(ctx);
+    std::vector<DevImage> imgs(s->n_images);
+    for (uint32_t i = 0; i < s->n_images; ++i) {
+        const rtw_image &im = s->images[i];
+        cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        CK(cudaMallocArray(&arr, &fd, im.width, im.height));
+        ctx->image_arrays.push_back(arr);
+        CK(cudaMemcpy2DToArray(arr, 0, 0, im.rgba8, (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyHostToDevice));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;  // nearest texel, as texture.zig:126-133; bilinear would smear the alpha test
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        ctx->image_tex.push_back(tex);
+        imgs[i] = DevImage{tex, im.width, im.height, 0, 0};
+    }
+
+    CK(ctx->prims_flat.upload(flat));
+    CK(ctx->prims_bvh.upload(leaf_order));
+    CK(ctx->bvh_prim_id.upload(bvh.order));
+    CK(ctx->prim_material.upload(prim_mat));
+    CK(ctx->nodes.upload(bvh.nodes));
+    CK(ctx->xforms.upload(xforms));
+    CK(ctx->bigs.upload(bigs));
+    CK(ctx->materials.upload(mats));
+    CK(ctx->textures.upload(texs));
+    CK(ctx->images.upload(imgs));
+    CK(ctx->perlins.upload(perl));
+    CK(ctx->raw_prims.upload(raw));
+    CK(ctx->raw_chains.upload(chains));
+
+    DevScene &d = ctx->scene;
+    d.prims_flat = ctx->prims_flat.p; d.prims_bvh = ctx->prims_bvh.p; d.bvh_prim_id = ctx->bvh_prim_id.p;
+    d.prim_material = ctx->prim_material.p; d.nodes = ctx->nodes.p; d.xforms = ctx->xforms.p; d.bigs = ctx->bigs.p;
+    d.materials = ctx->materials.p; d.textures = ctx->textures.p; d.images = ctx->images.p; d.perlins = ctx->perlins.p;
+    d.n_prims = n; d.n_nodes = (uint32_t)bvh.nodes.size(); d.n_xforms = (uint32_t)xforms.size();
+    d.n_materials = s->n_materials; d.n_textures = s->n_textures;
+    d.root_is_leaf = bvh.root_is_leaf ? 1u : 0u;
+    ctx->raw = RawScene{ctx->raw_prims.p, ctx->raw_chains.p, ctx->nodes.p, ctx->bvh_prim_id.p, n, d.root_is_leaf};
+    ctx->n_prims = n;
+    ctx->root_is_leaf = bvh.root_is_leaf;
+    ctx->stats.bvh_nodes = (uint32_t)bvh.nodes.size();
+    ctx->stats.bvh_depth = bvh.depth;
+    CK(cudaDeviceSynchronize());
+    ctx->stats.ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    ctx->have_scene = true;
+    return 0;
+}
+
+static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *p, float *d_accum,
+                           cudaStream_t st, bool timed) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!ctx->have_scene) return fail(ctx, 1, "no scene uploaded");
+    if (!cam || !p || !d_accum) return fail(ctx, 1, "null argument");
+    if (p->width == 0 || p->height == 0) return fail(ctx, 1, "empty image");
+    if (p->spp_end < p->spp_begin) return fail(ctx, 1, "spp_end < spp_begin");
+    if ((uint64_t)p->width * p->height > 0x7FFFFFFFull) return fail(ctx, 1, "image too large");
+    int variant = 0;
+    if (int rc = pick_variant(ctx, p->variant, &variant)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const bool stats = (p->flags & RTW_FLAG_COUNT_EVENTS) != 0;
+
+    DevRender rp{};
+    rp.width = p->width; rp.height = p->height;
+    rp.spp_begin = p->spp_begin; rp.spp_end = p->spp_end;
+    rp.max_depth = p->max_depth;
+    rp.seed_lo = (uint32_t)p->seed; rp.seed_hi = (uint32_t)(p->seed >> 32);
+    rp.bg_r = (float)p->background[0]; rp.bg_g = (float)p->background[1]; rp.bg_b = (float)p->background[2];
+    rp.accum = reinterpret_cast<float4 *>(d_accum);
+    rp.tile_counter = ctx->tile_counter.p;
+    rp.stats = ctx->stat_counters.p;
+    rp.tiles_x = (p->width + 7) / 8;
+    rp.n_tiles = rp.tiles_x * ((p->height + 3) / 4);
+
+    const size_t smem = variant == VAR_FLAT ? (size_t)ctx->n_prims * sizeof(DevPrim) : 0;
+    const int per_sm = megakernel_ctas_per_sm(variant, stats, smem);
+    if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (smem %zu B)", smem);
+    const int grid = per_sm * ctx->n_sms;
+
+    // Work items = tiles x sample chunks.  Enough items per resident warp that the end-of-kernel tail
+    // (warps idle while the last items finish) stays small.  RTW_SPP_CHUNK overrides (0 = one chunk:
+    // each pixel owned by one warp, deterministic summation order).
+    const uint32_t spp = p->spp_end - p->spp_begin;
+    uint32_t chunk = spp;
+    const char *env = getenv("RTW_SPP_CHUNK");
+    if (env && *env) {
+        const long v = atol(env);
+        chunk = v <= 0 ? spp : (uint32_t)v;
+    } else if (spp > 0) {
+        const uint64_t warps = (uint64_t)grid * 4;
+        const uint64_t want_items = warps * 48;
+        uint64_t chunks = (want_items + rp.n_tiles - 1) / rp.n_tiles;
+        chunks = std::max<uint64_t>(1, std::min<uint64_t>(chunks, spp / 16 ? spp / 16 : 1));
+        chunk = (uint32_t)((spp + chunks - 1) / chunks);
+    }
+    if (chunk == 0) chunk = 1;
+    rp.spp_chunk = chunk;
+    rp.n_chunks = spp ? (spp + chunk - 1) / chunk : 0;
+
+    if (spp == 0) { ctx->stats.n_launches = 0; return 0; }
+    if (stats) CK(cudaMemsetAsync(ctx->stat_counters.p, 0, ST_COUNT * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned int), st));
+    const DevCamera dc = lower_camera(cam);
+    if (timed) CK(cudaEventRecord(ctx->ev[0], st));
+    CK(launch_megakernel(variant, stats, ctx->scene, dc, rp, grid, st));
+    if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+    ctx->stats.n_launches = 1;
+    ctx->stats.variant_used = variant == VAR_FLAT ? RTW_VARIANT_MEGA_FLAT : RTW_VARIANT_MEGA_BVH;
+    return 0;
+}
+
+static int fetch_counters(rtw_ctx *ctx) {
+    unsigned long long h[ST_COUNT];
+    CK(cudaMemcpy(h, ctx->stat_counters.p, sizeof h, cudaMemcpyDeviceToHost));
+    rtw_stats &s = ctx->stats;
+    s.paths = h[ST_PATHS]; s.rays = h[ST_RAYS]; s.node_tests = h[ST_NODE_TESTS]; s.sphere_tests = h[ST_SPHERE_TESTS];
+    s.sphere_roots = h[ST_SPHERE_ROOTS]; s.moving_tests = h[ST_MOVING_TESTS]; s.rect_tests = h[ST_RECT_TESTS];
+    s.rect_accepts = h[ST_RECT_ACCEPTS]; s.xform_apps = h[ST_XFORM_APPS]; s.sphere_finalise = h[ST_SPHERE_FINAL];
+    s.scatter_diffuse = h[ST_SC_DIFFUSE]; s.scatter_metal = h[ST_SC_METAL]; s.scatter_dielectric = h[ST_SC_DIELECTRIC];
+    s.emit_hits = h[ST_EMIT]; s.tex_checker = h[ST_TEX_CHECKER]; s.tex_image = h[ST_TEX_IMAGE]; s.tex_noise = h[ST_TEX_NOISE];
+    s.nan_pixels = h[ST_NAN_PIXELS];
+    return 0;
+}
+
+int rtw_cuda_accumulate(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *p, float *d_accum, void *stream) {
+    return accumulate_impl(ctx, cam, p, d_accum, (cudaStream_t)stream, false);
+}
+
+int rtw_cuda_resolve_multi(rtw_ctx *ctx, const float *const *d_accums, uint32_t n_bufs, uint32_t width, uint32_t height,
+                           uint32_t spp_total, uint8_t *d_rgb8, void *stream) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!d_accums || !d_rgb8 || n_bufs == 0 || n_bufs > kMaxResolveBufs) return fail(ctx, 1, "bad buffer list");
+    if (width == 0 || height == 0 || spp_total == 0) return fail(ctx, 1, "empty image or spp_total == 0");
+    CK(cudaSetDevice(ctx->device));
+    ResolveArgs a{};
+    for (uint32_t i = 0; i < n_bufs; ++i) {
+        if (!d_accums[i]) return fail(ctx, 1, "accumulation buffer %u is null", i);
+        a.bufs[i] = reinterpret_cast<const float4 *>(d_accums[i]);
+    }
+    a.n_bufs = n_bufs; a.width = width; a.height = height;
+    a.scale = 1.0f / (float)spp_total;
+    a.rgb8 = d_rgb8;
+    a.nan_counter = ctx->stat_counters.p + ST_NAN_PIXELS;
+    CK(cudaMemsetAsync(a.nan_counter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    CK(launch_resolve(a, (cudaStream_t)stream));
+    return 0;
+}
+
+int rtw_cuda_resolve(rtw_ctx *ctx, const float *d_accum, uint32_t width, uint32_t height, uint32_t spp_total,
+                     uint8_t *d_rgb8, void *stream) {
+    const float *bufs[1] = {d_accum};
+    return rtw_cuda_resolve_multi(ctx, bufs, 1, width, height, spp_total, d_rgb8, stream);
+}
+
+int rtw_cuda_render(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *p, uint8_t *rgb8_out, float *accum_out) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!p || !rgb8_out) return fail(ctx, 1, "null argument");
+    if (p->width == 0 || p->height == 0) return fail(ctx, 1, "empty image");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)p->width * p->height;
+    if (ctx->accum.n != npx) { CK(ctx->accum.alloc(npx)); CK(ctx->rgb8.alloc(npx * 3)); }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->accum.p, 0, npx * sizeof(float4), st));
+    if (int rc = accumulate_impl(ctx, cam, p, reinterpret_cast<float *>(ctx->accum.p), st, true)) return rc;
+    const uint32_t spp = p->spp_end - p->spp_begin;
+    const uint32_t spp_total = p->spp_total ? p->spp_total : spp;
+    if (spp_total == 0) return fail(ctx, 1, "no samples to resolve");
+    CK(cudaEventRecord(ctx->ev[2], st));
+    if (int rc = rtw_cuda_resolve(ctx, reinterpret_cast<const float *>(ctx->accum.p), p->width, p->height, spp_total, ctx->rgb8.p, st)) return rc;
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaMemcpyAsync(rgb8_out, ctx->rgb8.p, npx * 3, cudaMemcpyDeviceToHost, st));
+    if (accum_out) CK(cudaMemcpyAsync(accum_out, ctx->accum.p, npx * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (spp > 0) { CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->stats.ms_trace = ms; } else ctx->stats.ms_trace = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    ctx->stats.ms_resolve = ms;
+    ctx->stats.n_launches += 1;
+    if (int rc = fetch_counters(ctx)) return rc;
+    if (!(p->flags & RTW_FLAG_COUNT_EVENTS)) {
+        const uint64_t nan = ctx->stats.nan_pixels;
+        const double mu = ctx->stats.ms_upload, mt = ctx->stats.ms_trace, mr = ctx->stats.ms_resolve;
+        const uint32_t nl = ctx->stats.n_launches, vu = ctx->stats.variant_used, bn = ctx->stats.bvh_nodes, bd = ctx->stats.bvh_depth;
+        ctx->stats = rtw_stats{};
+        ctx->stats.nan_pixels = nan; ctx->stats.ms_upload = mu; ctx->stats.ms_trace = mt; ctx->stats.ms_resolve = mr;
+        ctx->stats.n_launches = nl; ctx->stats.variant_used = vu; ctx->stats.bvh_nodes = bn; ctx->stats.bvh_depth = bd;
+        ctx->stats.paths = (uint64_t)npx * spp;
+    }
+    return 0;
+}
+
+static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_camera *cam, uint32_t width, uint32_t height,
+                      uint32_t precision, uint32_t variant_req, uint32_t *prim_id, double *t, double *normal, double *uv) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!ctx->have_scene) return fail(ctx, 1, "no scene uploaded");
+    if (!prim_id) return fail(ctx, 1, "prim_id is null");
+    if (precision != 0 && precision != 32 && precision != 64) return fail(ctx, 1, "precision must be 0, 32 or 64");
+    if (n == 0) return 0;
+    int variant = 0;
+    if (int rc = pick_variant(ctx, variant_req, &variant)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint32_t> d_id;
+    DevBuf<double> d_t, d_n, d_uv, d_rays;
+    DevBuf<float> f_rays, f_t, f_n, f_uv;
+    int rc = 0;
+    auto cleanup = [&]() { d_id.release(); d_t.release(); d_n.release(); d_uv.release(); d_rays.release(); f_rays.release(); f_t.release(); f_n.release(); f_uv.release(); };
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, 2, "%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+    CKP(d_id.alloc(n));
+    std::vector<double> host_rays;
+    if (precision == 0 && !rays) {
+        // production probe takes explicit rays: generate the parity-mode primary rays on the host in f64
+        host_rays.resize((size_t)n * 7);
+        for (uint32_t j = 0; j < height; ++j)
+            for (uint32_t i = 0; i < width; ++i) {
+                const double s = ((double)i + 0.5) / ((double)width - 1.0), tt = ((double)j + 0.5) / ((double)height - 1.0);
+                double *q = &host_rays[((size_t)j * width + i) * 7];
+                for (int a = 0; a < 3; ++a) {
+                    q[a] = cam->origin[a];
+                    q[3 + a] = cam->lower_left_corner[a] + cam->horizontal[a] * s + cam->vertical[a] * tt - cam->origin[a];
+                }
+                q[6] = cam->time0 + 0.5 * (cam->time1 - cam->time0);
+            }
+        rays = host_rays.data();
+    }
+    if (precision == 0) {
+        std::vector<float> fr((size_t)n * 7);
+        for (size_t k = 0; k < fr.size(); ++k) fr[k] = (float)rays[k];
+        CKP(f_rays.upload(fr));
+        CKP(f_t.alloc(n)); CKP(f_n.alloc((size_t)n * 3)); CKP(f_uv.alloc((size_t)n * 2));
+        CKP(launch_probe(variant, ctx->scene, n, f_rays.p, d_id.p, f_t.p, f_n.p, f_uv.p, st));
+        CKP(cudaStreamSynchronize(st));
+        std::vector<float> ht(n), hn((size_t)n * 3), hu((size_t)n * 2);
+        CKP(cudaMemcpy(prim_id, d_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CKP(cudaMemcpy(ht.data(), f_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        CKP(cudaMemcpy(hn.data(), f_n.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        CKP(cudaMemcpy(hu.data(), f_uv.p, (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (t) for (uint32_t k = 0; k < n; ++k) t[k] = ht[k];
+        if (normal) for (size_t k = 0; k < (size_t)n * 3; ++k) normal[k] = hn[k];
+        if (uv) for (size_t k = 0; k < (size_t)n * 2; ++k) uv[k] = hu[k];
+    } else {
+        RawCamera rc_cam{};
+        if (!rays) {
+            for (int a = 0; a < 3; ++a) {
+                rc_cam.origin[a] = cam->origin[a]; rc_cam.horizontal[a] = cam->horizontal[a];
+                rc_cam.vertical[a] = cam->vertical[a]; rc_cam.llc[a] = cam->lower_left_corner[a];
+            }
+            rc_cam.time0 = cam->time0; rc_cam.time1 = cam->time1;
+        } else {
+            std::vector<double> hr(rays, rays + (size_t)n * 7);
+            CKP(d_rays.upload(hr));
+        }
+        CKP(d_t.alloc(n)); CKP(d_n.alloc((size_t)n * 3)); CKP(d_uv.alloc((size_t)n * 2));
+        CKP(launch_ref_probe((int)precision, variant, ctx->raw, n, rays ? d_rays.p : nullptr, rays ? nullptr : &rc_cam, width,
+                             height, d_id.p, d_t.p, d_n.p, d_uv.p, st));
+        CKP(cudaStreamSynchronize(st));
+        CKP(cudaMemcpy(prim_id, d_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (t) CKP(cudaMemcpy(t, d_t.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (normal) CKP(cudaMemcpy(normal, d_n.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (uv) CKP(cudaMemcpy(uv, d_uv.p, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+#undef CKP
+    cleanup();
+    return 0;
+}
+
+int rtw_cuda_trace_rays(rtw_ctx *ctx, uint32_t n, const double *rays, uint32_t precision, uint32_t variant,
+                        uint32_t *prim_id, double *t, double *normal, double *uv) {
+    if (ctx && n && !rays) return fail(ctx, 1, "rays is null");
+    return probe_impl(ctx, n, rays, nullptr, 0, 0, precision, variant, prim_id, t, normal, uv);
+}
+
+int rtw_cuda_primary_hits(rtw_ctx *ctx, const rtw_camera *cam, uint32_t width, uint32_t height, uint32_t precision,
+                          uint32_t variant, uint32_t *prim_id, double *t, double *normal) {
+    if (ctx && !cam) return fail(ctx, 1, "camera is null");
+    if (ctx && ((uint64_t)width * height > 0x7FFFFFFFull)) return fail(ctx, 1, "image too large");
+    return probe_impl(ctx, width * height, nullptr, cam, width, height, precision, variant, prim_id, t, normal, nullptr);
+}
+
+int rtw_cuda_stats(rtw_ctx *ctx, rtw_stats *out) {
+    if (!ctx || !out) return fail(ctx, 1, "null argument");
+    *out = ctx->stats;
+    return 0;
+}
+
+int rtw_cuda_measure_fp32_peak(rtw_ctx *ctx, double *tflops, double *sm_clock_mhz) {
+    if (!ctx || !tflops) return fail(ctx, 1, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const int grid = ctx->n_sms * 8, iters = 4096;
+    DevBuf<float> out;
+    CK(out.alloc((size_t)grid * 256));
+    cudaStream_t st = ctx->stream;
+    CK(launch_ffma_peak(out.p, grid, 64, st));  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(launch_ffma_peak(out.p, grid, iters, st));
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        const double flops = (double)grid * 256 * iters * 16 * 8 * 2;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    out.release();
+    *tflops = best;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// rtw_device.cuh — device-side data layout of the flattened scene (all fp32, SoA-of-records).
+//
+// The reference keeps a tagged-union graph of f64 structs (src/rtw/hittable.zig:22-33,
+// material.zig:16-20, texture.zig:10-14).  On the device every table is an array of 32-byte
+// records so one record = one or two 16-byte vector loads (coalesced / broadcast friendly):
+//   DevPrim      2 x float4   primitives, either in reference order (flat scan) or BVH leaf order
+//   BvhNode      2 x float4   {min, a | max, b}; siblings adjacent -> one aligned 64-byte fetch
+//   DevXform     composed instance transform (Translate/RotateY chain, hittable.zig:472-596)
+//   DevBigSphere reference-point data for spheres whose radius makes |oc|^2 - r^2 cancel in fp32
+//   DevMaterial / DevTexture
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtw {
+
+constexpr uint32_t kMiss = 0xFFFFFFFFu;
+
+// prim.b.w (as uint) = kind | (extra << 8)
+enum : uint32_t { PK_SPHERE = 0, PK_XY = 2, PK_XZ = 3, PK_YZ = 4 };
+
+struct __align__(16) DevPrim {
+    // sphere: a = (cbx, cby, cbz, r)   centre(time) = cb + vel*time   (moving: hittable.zig:219-221)
+    //         b = (vx, vy, vz, meta)   meta = PK_SPHERE | (big_index+1) << 8
+    // rect:   a = (a0, a1, b0, b1)     in-plane bounds
+    //         b = (k, bits(xform index or -1), 0, meta)
+    float4 a, b;
+};
+
+struct __align__(16) BvhNode {
+    float mnx, mny, mnz;
+    uint32_t a;  // interior: index of left child (right = a+1); leaf: first slot
+    float mxx, mxy, mxz;
+    uint32_t b;  // interior: 0; leaf: primitive count (>0)
+};
+
+struct __align__(16) DevXform {
+    // object = A*world + t with A = rotation about Y: x' = c*x - s*z, z' = s*x + c*z
+    float c, s, tx, ty, tz, pad0, pad1, pad2;
+};
+
+struct __align__(16) DevBigSphere {
+    // o - centre = (o - q) + m, |o-centre|^2 - r^2 = |o-q|^2 + 2 (o-q).m + K, K = |m|^2 - r^2
+    float qx, qy, qz, K;
+    float mx, my, mz, pad;
+};
+
+struct __align__(16) DevMaterial {
+    uint32_t kind;  // RTW_MAT_*
+    int32_t tex;
+    float r, g, b;  // metal albedo
+    float param;    // fuzz | ir
+    float pad0, pad1;
+};
+
+struct __align__(16) DevTexture {
+    uint32_t kind;  // RTW_TEX_*
+    int32_t a, b;   // checker: odd, even; noise: perlin index; image: image index
+    float scale;
+    float r, g, bl;
+    uint32_t pad;
+};
+
+struct DevImage {
+    cudaTextureObject_t tex;  // uchar4, point filter, unnormalised coords, clamp
+    uint32_t w, h;
+    uint32_t pad0, pad1;
+};
+
+struct DevPerlin {
+    float4 ranvec[256];
+    uint8_t perm[3][256];
+};
+
+struct DevScene {
+    const DevPrim *prims_flat;    // reference order: slot == prim id
+    const DevPrim *prims_bvh;     // BVH leaf order
+    const uint32_t *bvh_prim_id;  // slot -> prim id
+    const uint32_t *prim_material;  // indexed by prim id
+    const BvhNode *nodes;
+    const DevXform *xforms;
+    const DevBigSphere *bigs;
+    const DevMaterial *materials;
+    const DevTexture *textures;
+    const DevImage *images;
+    const DevPerlin *perlins;
+    uint32_t n_prims, n_nodes, n_xforms, n_materials, n_textures;
+    uint32_t root_is_leaf;
+};
+
+struct DevCamera {  // src/main.zig:40-51, rounded to fp32
+    float ox, oy, oz;
+    float hx, hy, hz;
+    float vx, vy, vz;
+    float lx, ly, lz;
+    float ux, uy, uz;
+    float wx, wy, wz;  // camera v
+    float lens_radius, time0, time1;
+};
+
+// Event counters.  Order must match rtw_stats in include/rtw_cuda.h.
+enum StatSlot {
+    ST_PATHS = 0, ST_RAYS, ST_NODE_TESTS, ST_SPHERE_TESTS, ST_SPHERE_ROOTS, ST_MOVING_TESTS, ST_RECT_TESTS,
+    ST_RECT_ACCEPTS, ST_XFORM_APPS, ST_SPHERE_FINAL, ST_SC_DIFFUSE, ST_SC_METAL, ST_SC_DIELECTRIC, ST_EMIT,
+    ST_TEX_CHECKER, ST_TEX_IMAGE, ST_TEX_NOISE, ST_NAN_PIXELS, ST_COUNT
+};
+
+struct DevRender {
+    uint32_t width, height;
+    uint32_t spp_begin, spp_end;
+    uint32_t max_depth;
+    uint32_t seed_lo, seed_hi;
+    float bg_r, bg_g, bg_b;
+    float4 *accum;                 // width*height, row j = reference scanline j
+    unsigned int *tile_counter;    // persistent-kernel work queue
+    unsigned long long *stats;     // ST_COUNT counters (instrumented build only)
+    uint32_t n_tiles, tiles_x, spp_chunk, n_chunks;
+};
+
+}  // namespace rtw

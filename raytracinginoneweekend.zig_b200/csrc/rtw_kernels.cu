@@ -1,0 +1,272 @@
+// rtw_kernels.cu — production kernels (fp32, FMA contraction on), sm_100a.
+//
+//   k_megakernel<VARIANT,STATS>  K1: replaces the loop nest src/main.zig:382-394 and everything below it
+//   k_resolve                    K4: replaces src/main.zig:395-400 (average, sqrt, clamp, x256 -> u8, row flip),
+//                                    optionally summing several (peer-mapped) accumulation buffers first
+//   k_probe                      production-arithmetic closest-hit probe (parity instrument)
+//   k_ffma_peak                  FP32 roofline denominator, measured on the device
+//
+// Megakernel design.  The work is embarrassingly parallel, FP32/issue bound, with two sources of
+// SIMT inefficiency: paths of very different length (1..50 rays) and per-ray divergence in traversal
+// and material code.  The kernel is persistent: a grid of (#SMs x resident CTAs) CTAs pulls work items
+// (an 8x4 pixel tile x a chunk of samples) from an atomic queue.  Inside a warp, lane = pixel; each
+// lane runs a regenerate-on-terminate loop: when its path ends it immediately starts the next sample
+// of its own pixel, so lanes stay busy until the chunk's samples run out; per-pixel sums stay in
+// registers and are flushed once per work item.
+#include <cuda_runtime.h>
+
+#include "rtw_kernels.h"
+#include "rtw_trace.cuh"
+
+namespace rtw {
+
+constexpr int kBlock = 128;  // threads per CTA
+
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(kBlock) k_megakernel(const DevScene sc, const DevCamera cam, const DevRender rp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevPrim *s_prims = reinterpret_cast<DevPrim *>(smem_raw);
+    if (VARIANT == VAR_FLAT) {
+        // stage the primitive table once per CTA (reference order), 32 bytes per prim
+        const float4 *src = reinterpret_cast<const float4 *>(sc.prims_flat);
+        float4 *dst = reinterpret_cast<float4 *>(s_prims);
+        for (uint32_t i = threadIdx.x; i < sc.n_prims * 2; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    Counters<STATS> cn;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t total_items = rp.n_tiles * rp.n_chunks;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(rp.tile_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total_items) break;
+        // chunk-major order: all tiles of chunk 0 first, so concurrent warps rarely share a pixel
+        const uint32_t chunk = item / rp.n_tiles, tile = item - chunk * rp.n_tiles;
+        const uint32_t ty = tile / rp.tiles_x, tx = tile - ty * rp.tiles_x;
+        const uint32_t i = tx * 8 + (lane & 7), j = ty * 4 + (lane >> 3);
+        const bool inside = i < rp.width && j < rp.height;
+        const uint32_t pixel = j * rp.width + i;
+        uint32_t sample = rp.spp_begin + chunk * rp.spp_chunk;
+        const uint32_t sample_end = inside ? min(sample + rp.spp_chunk, rp.spp_end) : sample;
+
+        float3 sum = make_float3(0.0f, 0.0f, 0.0f);
+        float3 beta = make_float3(1.0f, 1.0f, 1.0f), L = make_float3(0.0f, 0.0f, 0.0f);
+        Ray r;
+        uint32_t bounce = 0, cur_sample = 0;
+        bool alive = false;
+        for (;;) {
+            if (!alive) {
+                if (sample < sample_end) {
+                    cur_sample = sample++;
+                    r = camera_ray(cam, rp, pixel, i, j, cur_sample);
+                    beta = make_float3(1.0f, 1.0f, 1.0f);
+                    L = make_float3(0.0f, 0.0f, 0.0f);
+                    bounce = 0;
+                    alive = true;
+                    cn.add(ST_PATHS);
+                }
+            }
+            if (!__any_sync(0xffffffffu, alive)) break;
+            if (alive) {
+                cn.add(ST_RAYS);
+                Hit h;
+                if (VARIANT == VAR_FLAT) h = closest_hit_flat<STATS>(r, s_prims, sc.n_prims, sc, 0.001f, cn);
+                else h = closest_hit_bvh<STATS>(r, sc, 0.001f, cn);
+                if (h.slot == kMiss) {  // main.zig:109-112
+                    L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
+                    alive = false;
+                } else {
+                    DevPrim prim;
+                    uint32_t prim_id;
+                    if (VARIANT == VAR_FLAT) { prim = s_prims[h.slot]; prim_id = h.slot; }
+                    else { prim = sc.prims_bvh[h.slot]; prim_id = sc.bvh_prim_id[h.slot]; }
+                    ++bounce;
+                    alive = shade<STATS>(sc, rp, r, prim, prim_id, h.t, pixel, cur_sample, bounce, beta, L, cn);
+                    // depth exhausted: the next rayColor call returns black before intersecting (main.zig:105-108)
+                    if (bounce >= rp.max_depth) alive = false;
+                }
+                if (!alive) { sum.x += L.x; sum.y += L.y; sum.z += L.z; }
+            }
+        }
+        if (inside) {
+            float4 *dst = rp.accum + pixel;
+            const float ns = (float)(sample_end - (rp.spp_begin + chunk * rp.spp_chunk));
+            if (rp.n_chunks == 1) {  // this warp owns the pixel: plain read-modify-write, deterministic
+                float4 a = *dst;
+                a.x += sum.x; a.y += sum.y; a.z += sum.z; a.w += ns;
+                *dst = a;
+            } else {
+                atomicAdd(&dst->x, sum.x); atomicAdd(&dst->y, sum.y); atomicAdd(&dst->z, sum.z); atomicAdd(&dst->w, ns);
+            }
+        }
+    }
+    if (STATS) cn.flush(rp.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 resolve: out = 256 * clamp(sqrt(sum / spp), 0, 0.999) truncated to u8, written to row H-1-j.
+// Sums up to kMaxResolveBufs accumulation buffers first; with peer access enabled those may live on
+// other GPUs, i.e. the cross-GPU reduction and the resolve are one kernel over NVLink peer memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t quantise(float sum, float scale, unsigned int &nan_flag) {
+    float c = sqrtf(sum * scale);
+    if (!(c == c)) { c = 0.0f; nan_flag = 1u; }  // reference: UB on NaN; here 0
+    c = fminf(fmaxf(c, 0.0f), 0.999f);
+    return (uint32_t)(256.0f * c);
+}
+
+__global__ void __launch_bounds__(256) k_resolve(ResolveArgs a) {
+    const uint32_t n = a.width * a.height;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int nan_flag = 0u;
+    if (idx < n) {
+        float4 s = __ldcs(a.bufs[0] + idx);
+        for (uint32_t b = 1; b < a.n_bufs; ++b) {
+            const float4 q = __ldcs(a.bufs[b] + idx);
+            s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+        }
+        const uint32_t j = idx / a.width, i = idx - j * a.width;
+        uint8_t *o = a.rgb8 + ((size_t)(a.height - 1u - j) * a.width + i) * 3u;
+        o[0] = (uint8_t)quantise(s.x, a.scale, nan_flag);
+        o[1] = (uint8_t)quantise(s.y, a.scale, nan_flag);
+        o[2] = (uint8_t)quantise(s.z, a.scale, nan_flag);
+    }
+    if (a.nan_counter) {
+        const unsigned int m = __ballot_sync(0xffffffffu, nan_flag != 0u);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(a.nan_counter, (unsigned long long)__popc(m));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Production-arithmetic probe: closest hit of explicit rays with exactly the code the megakernel
+// runs (robust sphere form, FMA contraction on).
+// ---------------------------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n, const float *__restrict__ rays,
+                                                  uint32_t *prim_id, float *t_out, float *normal, float *uv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevPrim *s_prims = reinterpret_cast<DevPrim *>(smem_raw);
+    if (VARIANT == VAR_FLAT) {
+        const float4 *src = reinterpret_cast<const float4 *>(sc.prims_flat);
+        float4 *dst = reinterpret_cast<float4 *>(s_prims);
+        for (uint32_t i = threadIdx.x; i < sc.n_prims * 2; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float *q = rays + 7 * (size_t)idx;
+    Ray r{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+    Counters<false> cn;
+    Hit h;
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, s_prims, sc.n_prims, sc, 0.001f, cn);
+    else h = closest_hit_bvh<false>(r, sc, 0.001f, cn);
+    if (h.slot == kMiss) {
+        prim_id[idx] = kMiss; t_out[idx] = 0.0f;
+        normal[3 * idx] = normal[3 * idx + 1] = normal[3 * idx + 2] = 0.0f;
+        if (uv) { uv[2 * idx] = 0.0f; uv[2 * idx + 1] = 0.0f; }
+        return;
+    }
+    DevPrim prim;
+    uint32_t id;
+    if (VARIANT == VAR_FLAT) { prim = s_prims[h.slot]; id = h.slot; }
+    else { prim = sc.prims_bvh[h.slot]; id = sc.bvh_prim_id[h.slot]; }
+    const Surface s = finalise_hit<false>(r, prim, h.t, sc, cn);
+    prim_id[idx] = id; t_out[idx] = h.t;
+    normal[3 * idx] = s.nx; normal[3 * idx + 1] = s.ny; normal[3 * idx + 2] = s.nz;
+    if (uv) {
+        float u = s.u, v = s.v;
+        if (s.is_sphere) {
+            const float pi = 3.14159265358979323846f;
+            u = (atan2f(-s.onz, s.onx) + pi) / (2.0f * pi);
+            v = acosf(fminf(fmaxf(-s.ony, -1.0f), 1.0f)) / pi;
+        }
+        uv[2 * idx] = u; uv[2 * idx + 1] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 peak: 8 independent FFMA chains per thread, 2 flops per FFMA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (called from rtw_api.cpp through rtw_kernels.h)
+// ---------------------------------------------------------------------------------------------
+template <int VARIANT, bool STATS>
+static cudaError_t launch_mega_t(const DevScene &sc, const DevCamera &cam, const DevRender &rp, int grid,
+                                 size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_megakernel<VARIANT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_megakernel<VARIANT, STATS><<<grid, kBlock, smem, st>>>(sc, cam, rp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_megakernel(int variant, bool stats, const DevScene &sc, const DevCamera &cam, const DevRender &rp,
+                              int grid, cudaStream_t st) {
+    const size_t smem = variant == VAR_FLAT ? (size_t)sc.n_prims * sizeof(DevPrim) : 0;
+    if (variant == VAR_FLAT) return stats ? launch_mega_t<VAR_FLAT, true>(sc, cam, rp, grid, smem, st)
+                                          : launch_mega_t<VAR_FLAT, false>(sc, cam, rp, grid, smem, st);
+    return stats ? launch_mega_t<VAR_BVH, true>(sc, cam, rp, grid, smem, st)
+                 : launch_mega_t<VAR_BVH, false>(sc, cam, rp, grid, smem, st);
+}
+
+int megakernel_ctas_per_sm(int variant, bool stats, size_t smem) {
+    int n = 0;
+    cudaError_t e;
+    if (variant == VAR_FLAT) {
+        if (smem > 48 * 1024) {
+            if (stats) cudaFuncSetAttribute(k_megakernel<VAR_FLAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else cudaFuncSetAttribute(k_megakernel<VAR_FLAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        e = stats ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_FLAT, true>, kBlock, smem)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_FLAT, false>, kBlock, smem);
+    } else {
+        e = stats ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_BVH, true>, kBlock, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_BVH, false>, kBlock, 0);
+    }
+    return e == cudaSuccess ? n : 0;
+}
+
+cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st) {
+    const uint32_t n = a.width * a.height;
+    k_resolve<<<(n + 255) / 256, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe(int variant, const DevScene &sc, uint32_t n, const float *rays, uint32_t *prim_id, float *t,
+                         float *normal, float *uv, cudaStream_t st) {
+    const int grid = (int)((n + kBlock - 1) / kBlock);
+    if (variant == VAR_FLAT) {
+        const size_t smem = (size_t)sc.n_prims * sizeof(DevPrim);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_probe<VAR_FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_probe<VAR_FLAT><<<grid, kBlock, smem, st>>>(sc, n, rays, prim_id, t, normal, uv);
+    } else {
+        k_probe<VAR_BVH><<<grid, kBlock, 0, st>>>(sc, n, rays, prim_id, t, normal, uv);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ffma_peak(float *out, int grid, int iters, cudaStream_t st) {
+    k_ffma_peak<<<grid, 256, 0, st>>>(out, iters, 1.0000001f, 1e-9f);
+    return cudaGetLastError();
+}
+
+}  // namespace rtw

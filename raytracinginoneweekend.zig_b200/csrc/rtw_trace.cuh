@@ -1,0 +1,510 @@
+// rtw_trace.cuh — production fp32 device code: RNG, closest-hit (flat scan and BVH), shading.
+//
+// What each piece replaces in the reference (all f64 there, fp32 here):
+//   Philox4x32-10 + samplers  <- the single sequential Xoshiro stream and the rejection samplers
+//                                 (src/main.zig:300-301, src/rtw/rand.zig:13-40)
+//   closest_hit_flat          <- HittableList.hit linear scan (src/rtw/hittable.zig:231-244)
+//   closest_hit_bvh           <- new (the reference has no BVH; Aabb.hit aabb.zig:8-45 is dead code)
+//   sphere_test / rect_test   <- Sphere.hit / MovingSphere.hit / *Rect.hit (hittable.zig:95-131,
+//                                 165-201, 278-303, 331-356, 384-409)
+//   finalise_hit              <- the HitRecord fill of those functions + Translate/RotateY back-map
+//   shade                     <- Material.emitted/scatter (material.zig:16-121), Texture.value
+//                                 (texture.zig:36-145), one level of rayColor (main.zig:103-122)
+#pragma once
+#include "rtw_device.cuh"
+
+namespace rtw {
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10.  key = (seed_lo, seed_hi), counter = (pixel, sample, block, 0).
+// block 0 = camera ray, block b>=1 = bounce b.  Every draw of a (pixel, sample, bounce) is a pure
+// function of its indices, so any partition of the samples over threads/GPUs gives the same paths.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0);
+        k0 += W0;
+        k1 += W1;
+    }
+    return ctr;
+}
+// 24-bit uniform in [0,1): exactly the fp32 lattice, never 1.0
+__device__ __forceinline__ float u01_24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, time;
+};
+
+struct Hit {
+    float t;
+    uint32_t slot;  // index into the prim array that was searched; kMiss = no hit
+};
+
+template <bool STATS>
+struct Counters {
+    __device__ __forceinline__ void add(int, uint32_t = 1) {}
+    __device__ __forceinline__ void flush(unsigned long long *) {}
+};
+template <>
+struct Counters<true> {
+    uint32_t c[ST_COUNT];
+    __device__ Counters() {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; ++i) c[i] = 0;
+    }
+    __device__ __forceinline__ void add(int slot, uint32_t n = 1) { c[slot] += n; }
+    __device__ void flush(unsigned long long *g) {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; ++i) {
+            unsigned long long v = c[i];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(g + i, v);
+            c[i] = 0;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Primitive tests.  `inv_a` = 1/(d.d), `add` = d.d of the (un-normalised, main.zig:94) direction.
+// Accept rule = the reference's: nearest root in [t_min, t_max], both ends inclusive
+// (hittable.zig:106-116).
+// ---------------------------------------------------------------------------------------------
+// Sphere: numerically robust fp32 form.  The textbook b^2 - a*c of hittable.zig:96-101 cancels
+// catastrophically in fp32 for small far spheres (measured: -0.5 % image bias from false
+// self-intersections); instead the discriminant comes from the perpendicular offset l of the
+// centre from the ray line (disc' = r^2 - |l|^2), and the roots from q = b' + sign(b') sqrt(a disc'),
+// t = {c/q, q/a}.  Same roots in exact arithmetic.
+template <bool STATS>
+__device__ __forceinline__ bool sphere_test(const Ray &r, float add, float inv_a, const DevPrim &p,
+                                            const DevBigSphere *bigs, float t_min, float t_max, float &t_out,
+                                            Counters<STATS> &cn) {
+    cn.add(ST_SPHERE_TESTS);
+    const float cx = fmaf(p.b.x, r.time, p.a.x), cy = fmaf(p.b.y, r.time, p.a.y), cz = fmaf(p.b.z, r.time, p.a.z);
+    const float ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
+    const float bp = fmaf(ocx, r.dx, fmaf(ocy, r.dy, ocz * r.dz));
+    const float k = bp * inv_a;
+    const float lx = fmaf(-k, r.dx, ocx), ly = fmaf(-k, r.dy, ocy), lz = fmaf(-k, r.dz, ocz);
+    const float rr = p.a.w * p.a.w;
+    const float discp = fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, rr)));
+    if (discp < 0.0f) return false;
+    cn.add(ST_SPHERE_ROOTS);
+    float c;
+    const uint32_t big = __float_as_uint(p.b.w) >> 8;
+    if (big) {
+        // |o-c|^2 - r^2 about a reference point q on the surface: no 1e6 - 1e6 cancellation for the
+        // r=1000 ground sphere of main.zig:172.
+        const DevBigSphere g = bigs[big - 1];
+        const float ax = r.ox - g.qx, ay = r.oy - g.qy, az = r.oz - g.qz;
+        const float aa = fmaf(ax, ax, fmaf(ay, ay, az * az));
+        const float am = fmaf(ax, g.mx, fmaf(ay, g.my, az * g.mz));
+        c = fmaf(2.0f, am, aa) + g.K;
+    } else {
+        c = fmaf(ocx, ocx, fmaf(ocy, ocy, fmaf(ocz, ocz, -rr)));
+    }
+    const float sq = sqrtf(add * discp);
+    const float bq = -bp;
+    const float q = bq + copysignf(sq, bq);
+    const float t0 = __fdividef(c, q), t1 = q * inv_a;
+    const float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
+    float root = lo;
+    if (root < t_min || t_max < root) {
+        root = hi;
+        if (root < t_min || t_max < root) return false;
+    }
+    if (!(root == root)) return false;  // q == 0 (ray through the centre of a zero-disc sphere)
+    t_out = root;
+    return true;
+}
+
+// Axis-aligned rect in its object space.  kind: PK_XY (k on z), PK_XZ (k on y), PK_YZ (k on x).
+__device__ __forceinline__ bool rect_test_os(uint32_t kind, float ox, float oy, float oz, float dx, float dy,
+                                             float dz, const DevPrim &p, float t_min, float t_max, float &t_out) {
+    float ok, dk, oa, da, ob, db;
+    if (kind == PK_XY) { ok = oz; dk = dz; oa = ox; da = dx; ob = oy; db = dy; }
+    else if (kind == PK_XZ) { ok = oy; dk = dy; oa = ox; da = dx; ob = oz; db = dz; }
+    else { ok = ox; dk = dx; oa = oy; da = dy; ob = oz; db = dz; }
+    const float t = (p.b.x - ok) / dk;  // IEEE division, as hittable.zig:279
+    if (t < t_min || t > t_max) return false;
+    const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
+    if (pa < p.a.x || pa > p.a.y || pb < p.a.z || pb > p.a.w) return false;
+    t_out = t;
+    return true;
+}
+
+template <bool STATS>
+__device__ __forceinline__ bool rect_test(const Ray &r, const DevPrim &p, uint32_t kind, const DevXform *xforms,
+                                          float t_min, float t_max, float &t_out, Counters<STATS> &cn) {
+    cn.add(ST_RECT_TESTS);
+    const int xi = __float_as_int(p.b.y);
+    float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+    if (xi >= 0) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
+        cn.add(ST_XFORM_APPS);
+        const DevXform x = xforms[xi];
+        const float wx = ox, wz = oz, vx = dx, vz = dz;
+        ox = fmaf(x.c, wx, -x.s * wz) + x.tx;
+        oy = oy + x.ty;
+        oz = fmaf(x.s, wx, x.c * wz) + x.tz;
+        dx = fmaf(x.c, vx, -x.s * vz);
+        dz = fmaf(x.s, vx, x.c * vz);
+    }
+    const bool h = rect_test_os(kind, ox, oy, oz, dx, dy, dz, p, t_min, t_max, t_out);
+    if (h) cn.add(ST_RECT_ACCEPTS);
+    return h;
+}
+
+template <bool STATS>
+__device__ __forceinline__ bool prim_test(const Ray &r, float add, float inv_a, const DevPrim &p,
+                                          const DevScene &sc, float t_min, float t_max, float &t_out,
+                                          Counters<STATS> &cn) {
+    const uint32_t kind = __float_as_uint(p.b.w) & 0xFFu;
+    if (kind == PK_SPHERE) return sphere_test<STATS>(r, add, inv_a, p, sc.bigs, t_min, t_max, t_out, cn);
+    return rect_test<STATS>(r, p, kind, sc.xforms, t_min, t_max, t_out, cn);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flat scan: prims staged in shared memory in REFERENCE ORDER; every lane reads the same record
+// (smem broadcast), so the scan itself has no divergence.  Sequential scan with inclusive t_max
+// reproduces the reference's tie rule (later element wins) for free.
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const DevPrim *s_prims, uint32_t n, const DevScene &sc,
+                                                float t_min, Counters<STATS> &cn) {
+    const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
+    const float inv_a = 1.0f / add;
+    Hit h{__int_as_float(0x7f800000), kMiss};
+    for (uint32_t i = 0; i < n; ++i) {
+        const DevPrim p = s_prims[i];
+        float t;
+        if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
+            h.t = t;
+            h.slot = i;
+        }
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH traversal: binary BVH, 32-byte nodes, siblings adjacent (one 64-byte aligned fetch per
+// step), ordered descent, per-thread stack.  Slab test = aabb.zig:8-45 with 1/d precomputed and
+// the far bound widened by 2 ulps so rounding can never cull a box holding an acceptable hit.
+// Ties: a candidate replaces the current hit if t < best, or t == best and its prim id is larger
+// (= "later list element wins", hittable.zig:235-242).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool slab(const BvhNode &n, const Ray &r, float idx, float idy, float idz, float t_min,
+                                     float t_max, float &t_near) {
+    const float x0 = (n.mnx - r.ox) * idx, x1 = (n.mxx - r.ox) * idx;
+    const float y0 = (n.mny - r.oy) * idy, y1 = (n.mxy - r.oy) * idy;
+    const float z0 = (n.mnz - r.oz) * idz, z1 = (n.mxz - r.oz) * idz;
+    // fminf/fmaxf drop NaNs (0*inf when the origin lies on a slab plane of a parallel ray)
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+    t_near = tn;
+    return tn <= tf * 1.0000004f;
+}
+
+constexpr int kBvhStack = 48;
+
+template <bool STATS>
+__device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+    const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
+    const float inv_a = 1.0f / add;
+    const float idx = 1.0f / r.dx, idy = 1.0f / r.dy, idz = 1.0f / r.dz;
+    Hit h{__int_as_float(0x7f800000), kMiss};
+    uint32_t best_id = 0;
+    uint32_t stack[kBvhStack];
+    int sp = 0;
+    const BvhNode *__restrict__ nodes = sc.nodes;
+    auto leaf = [&](uint32_t first, uint32_t count) {
+        for (uint32_t i = 0; i < count; ++i) {
+            const uint32_t slot = first + i;
+            const DevPrim p = sc.prims_bvh[slot];
+            float t;
+            if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
+                if (t < h.t || h.slot == kMiss) {
+                    h.t = t; h.slot = slot; best_id = sc.bvh_prim_id[slot];
+                } else {  // t == h.t
+                    const uint32_t id = sc.bvh_prim_id[slot];
+                    if (id > best_id) { h.slot = slot; best_id = id; }
+                }
+            }
+        }
+    };
+    if (sc.root_is_leaf) {
+        const BvhNode n = nodes[0];
+        leaf(n.a, n.b);
+        return h;
+    }
+    uint32_t cur = nodes[0].a;  // index of the root's left child; right = cur+1
+    for (;;) {
+        const float4 *q = reinterpret_cast<const float4 *>(nodes + cur);
+        const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+        const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
+        const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
+        cn.add(ST_NODE_TESTS, 2);
+        float tl, tr;
+        bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
+        bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
+        // leaves are tested immediately; interiors are queued
+        if (hl && L.b) { leaf(L.a, L.b); hl = false; hr = hr && tr <= h.t; }
+        if (hr && R.b) { leaf(R.a, R.b); hr = false; hl = hl && tl <= h.t; }
+        if (hl && hr) {
+            const bool left_first = tl <= tr;
+            if (sp < kBvhStack) stack[sp++] = left_first ? R.a : L.a;
+            cur = left_first ? L.a : R.a;
+        } else if (hl) {
+            cur = L.a;
+        } else if (hr) {
+            cur = R.a;
+        } else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hit record of the winning primitive (computed once per ray, not per candidate as the reference
+// does at hittable.zig:118-128).
+// ---------------------------------------------------------------------------------------------
+struct Surface {
+    float px, py, pz;     // hit point, world space
+    float nx, ny, nz;     // face-corrected normal (HitRecord.normal)
+    float onx, ony, onz;  // outward normal (for sphere uv, hittable.zig:127)
+    float u, v;           // rect uv; sphere uv is computed lazily by the image texture
+    bool front_face;
+    bool is_sphere;
+};
+
+template <bool STATS>
+__device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, float t, const DevScene &sc,
+                                                Counters<STATS> &cn) {
+    Surface s;
+    const uint32_t kind = __float_as_uint(p.b.w) & 0xFFu;
+    s.px = fmaf(t, r.dx, r.ox); s.py = fmaf(t, r.dy, r.oy); s.pz = fmaf(t, r.dz, r.oz);  // Ray.at ray.zig:10-12
+    if (kind == PK_SPHERE) {
+        cn.add(ST_SPHERE_FINAL);
+        const float cx = fmaf(p.b.x, r.time, p.a.x), cy = fmaf(p.b.y, r.time, p.a.y), cz = fmaf(p.b.z, r.time, p.a.z);
+        const float inv_r = 1.0f / p.a.w;
+        s.onx = (s.px - cx) * inv_r; s.ony = (s.py - cy) * inv_r; s.onz = (s.pz - cz) * inv_r;
+        s.is_sphere = true;
+        s.u = 0.0f; s.v = 0.0f;
+    } else {
+        // object-space rect: outward normal is the +axis (hittable.zig:295-301), uv = normalised
+        // in-plane coordinates (hittable.zig:288-289)
+        const int xi = __float_as_int(p.b.y);
+        float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+        DevXform x{1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
+        if (xi >= 0) {
+            x = sc.xforms[xi];
+            const float wx = ox, wz = oz, vx = dx, vz = dz;
+            ox = fmaf(x.c, wx, -x.s * wz) + x.tx; oy = oy + x.ty; oz = fmaf(x.s, wx, x.c * wz) + x.tz;
+            dx = fmaf(x.c, vx, -x.s * vz); dz = fmaf(x.s, vx, x.c * vz);
+        }
+        const float qx = fmaf(t, dx, ox), qy = fmaf(t, dy, oy), qz = fmaf(t, dz, oz);
+        float pa, pb, nxo = 0.0f, nyo = 0.0f, nzo = 0.0f;
+        if (kind == PK_XY) { pa = qx; pb = qy; nzo = 1.0f; }
+        else if (kind == PK_XZ) { pa = qx; pb = qz; nyo = 1.0f; }
+        else { pa = qy; pb = qz; nxo = 1.0f; }
+        s.u = (pa - p.a.x) / (p.a.y - p.a.x);
+        s.v = (pb - p.a.z) / (p.a.w - p.a.z);
+        // object -> world for the normal (RotateY.hit hittable.zig:588-590): n = A^T n_obj
+        s.onx = fmaf(x.c, nxo, x.s * nzo);
+        s.ony = nyo;
+        s.onz = fmaf(-x.s, nxo, x.c * nzo);
+        s.is_sphere = false;
+    }
+    s.front_face = fmaf(s.onx, r.dx, fmaf(s.ony, r.dy, s.onz * r.dz)) < 0.0f;
+    const float sg = s.front_face ? 1.0f : -1.0f;
+    s.nx = sg * s.onx; s.ny = sg * s.ony; s.nz = sg * s.onz;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Textures — Texture.value texture.zig:36-145
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float perlin_noise(const DevPerlin &pn, float x, float y, float z) {  // perlin.zig:47-77,103-124
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    const float u = x - fx, v = y - fy, w = z - fz;
+    const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const uint32_t idx = pn.perm[0][(i + di) & 255] ^ pn.perm[1][(j + dj) & 255] ^ pn.perm[2][(k + dk) & 255];
+                const float4 c = pn.ranvec[idx];
+                const float wx = di ? uu : 1.0f - uu, wy = dj ? vv : 1.0f - vv, wz = dk ? ww : 1.0f - ww;
+                accum += wx * wy * wz * (c.x * (u - di) + c.y * (v - dj) + c.z * (w - dk));
+            }
+    return accum;
+}
+__device__ __forceinline__ float perlin_turb(const DevPerlin &pn, float x, float y, float z) {  // perlin.zig:79-91, depth 7
+    float accum = 0.0f, weight = 1.0f;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) {
+        accum += weight * perlin_noise(pn, x, y, z);
+        weight *= 0.5f;
+        x *= 2.0f; y *= 2.0f; z *= 2.0f;
+    }
+    return fabsf(accum);
+}
+
+template <bool STATS>
+__device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, const Surface &s, Counters<STATS> &cn) {
+    DevTexture tx = sc.textures[ti];
+    // Checker (texture.zig:79-82): sign(sin(10x) sin(10y) sin(10z)) < 0 -> odd.  sin(10 x) < 0 iff
+    // floor(10 x / pi) is odd, so the sign of the product is the parity of the three floors: the
+    // same function except on the measure-zero cell boundaries, without three sin evaluations.
+    // Children are textures themselves (texture.zig:59-60): loop handles nesting.
+    for (int guard = 0; tx.kind == 1u && guard < 8; ++guard) {
+        cn.add(ST_TEX_CHECKER);
+        const float k = 3.18309886183790672f;  // 10/pi
+        const int par = (int)floorf(s.px * k) + (int)floorf(s.py * k) + (int)floorf(s.pz * k);
+        tx = sc.textures[(par & 1) ? tx.a : tx.b];
+    }
+    if (tx.kind == 0u) return make_float3(tx.r, tx.g, tx.bl);  // solid texture.zig:46-55
+    if (tx.kind == 2u) {  // noise texture.zig:100-104
+        cn.add(ST_TEX_NOISE);
+        const float v = 0.5f * (1.0f + sinf(tx.scale * s.pz + 10.0f * perlin_turb(sc.perlins[tx.a], s.px, s.py, s.pz)));
+        return make_float3(v, v, v);
+    }
+    // image texture.zig:121-144 — nearest texel by truncation, alpha==0 -> (0,0,1)
+    cn.add(ST_TEX_IMAGE);
+    float u = s.u, v = s.v;
+    if (s.is_sphere) {  // getSphereUv hittable.zig:145-150
+        const float pi = 3.14159265358979323846f;
+        u = (atan2f(-s.onz, s.onx) + pi) / (2.0f * pi);
+        v = acosf(fminf(fmaxf(-s.ony, -1.0f), 1.0f)) / pi;
+    }
+    const DevImage im = sc.images[tx.a];
+    const float uc = fminf(fmaxf(u, 0.0f), 1.0f);
+    const float vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+    int i = (int)(uc * (float)im.w), j = (int)(vc * (float)im.h);
+    i = min(i, (int)im.w - 1);
+    j = min(j, (int)im.h - 1);  // reference clamps with width-1 (texture.zig:130, OOB bug): fixed
+    const uchar4 px = tex2D<uchar4>(im.tex, (float)i + 0.5f, (float)j + 0.5f);
+    if (px.w == 0) return make_float3(0.0f, 0.0f, 1.0f);
+    const float cs = 1.0f / 255.0f;
+    return make_float3(cs * px.x, cs * px.y, cs * px.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Samplers: same distributions as rand.zig:22-40, rejection-free (no divergent loops).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 sample_unit_vector(float u1, float u2) {  // randomUnitVector rand.zig:38-40
+    const float z = 1.0f - 2.0f * u1;
+    const float rxy = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float sn, cs;
+    __sincosf(6.28318530717958647692f * u2, &sn, &cs);
+    return make_float3(rxy * cs, rxy * sn, z);
+}
+__device__ __forceinline__ float3 sample_unit_ball(float u1, float u2, float u3) {  // randomPointInUnitSphere rand.zig:22-28
+    const float3 d = sample_unit_vector(u1, u2);
+    const float rad = cbrtf(u3);
+    return make_float3(d.x * rad, d.y * rad, d.z * rad);
+}
+__device__ __forceinline__ float2 sample_unit_disk(float u1, float u2) {  // randomPointInUnitDisk rand.zig:30-36
+    const float rad = sqrtf(u1);
+    float sn, cs;
+    __sincosf(6.28318530717958647692f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+// Camera.getRay main.zig:91-100 + the (u,v) jitter of main.zig:390-391.  One Philox block: five
+// 24-bit uniforms sliced out of its 128 bits.
+__device__ __forceinline__ Ray camera_ray(const DevCamera &cam, const DevRender &rp, uint32_t pixel, uint32_t i,
+                                          uint32_t j, uint32_t sample) {
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.seed_lo, rp.seed_hi);
+    const float ju = u01_24(rn.x), jv = u01_24(rn.y);
+    const float l1 = u01_24(rn.z), l2 = u01_24(rn.w);
+    const float tm = u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8));
+    const float s = ((float)i + ju) / ((float)rp.width - 1.0f);
+    const float t = ((float)j + jv) / ((float)rp.height - 1.0f);
+    const float2 dk = sample_unit_disk(l1, l2);
+    const float rdx = dk.x * cam.lens_radius, rdy = dk.y * cam.lens_radius;
+    const float offx = cam.ux * rdx + cam.wx * rdy, offy = cam.uy * rdx + cam.wy * rdy, offz = cam.uz * rdx + cam.wz * rdy;
+    Ray r;
+    r.ox = cam.ox + offx; r.oy = cam.oy + offy; r.oz = cam.oz + offz;
+    r.dx = fmaf(cam.vx, t, fmaf(cam.hx, s, cam.lx)) - cam.ox - offx;
+    r.dy = fmaf(cam.vy, t, fmaf(cam.hy, s, cam.ly)) - cam.oy - offy;
+    r.dz = fmaf(cam.vz, t, fmaf(cam.hz, s, cam.lz)) - cam.oz - offz;
+    r.time = fmaf(tm, cam.time1 - cam.time0, cam.time0);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One level of rayColor (main.zig:103-122) made iterative: `beta` is the product of attenuations
+// so far, `L` the radiance gathered.  Returns true when the path continues with `r` replaced by the
+// scattered ray.
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, Ray &r, const DevPrim &prim,
+                                      uint32_t prim_id, float t, uint32_t pixel, uint32_t sample, uint32_t bounce,
+                                      float3 &beta, float3 &L, Counters<STATS> &cn) {
+    const Surface s = finalise_hit<STATS>(r, prim, t, sc, cn);
+    const DevMaterial m = sc.materials[sc.prim_material[prim_id]];
+    if (m.kind == 3u) {  // diffuse_light: emitted on both faces, never scatters (material.zig:97-109)
+        cn.add(ST_EMIT);
+        const float3 e = texture_value<STATS>(sc, m.tex, s, cn);
+        L.x = fmaf(beta.x, e.x, L.x); L.y = fmaf(beta.y, e.y, L.y); L.z = fmaf(beta.z, e.z, L.z);
+        return false;
+    }
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.seed_lo, rp.seed_hi);
+    float ndx, ndy, ndz;
+    if (m.kind == 0u) {  // diffuse material.zig:44-52
+        cn.add(ST_SC_DIFFUSE);
+        const float3 uv = sample_unit_vector(u01_24(rn.x), u01_24(rn.y));
+        ndx = s.nx + uv.x; ndy = s.ny + uv.y; ndz = s.nz + uv.z;
+        if (fabsf(ndx) < 1e-8f && fabsf(ndy) < 1e-8f && fabsf(ndz) < 1e-8f) { ndx = s.nx; ndy = s.ny; ndz = s.nz; }
+        const float3 a = texture_value<STATS>(sc, m.tex, s, cn);
+        beta.x *= a.x; beta.y *= a.y; beta.z *= a.z;
+    } else {
+        const float dd = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
+        const float inv_len = dd > 0.0f ? rsqrtf(dd) : 1.0f;  // Vec3.normalized vec.zig:33-40
+        const float ux = r.dx * inv_len, uy = r.dy * inv_len, uz = r.dz * inv_len;
+        const float udn = fmaf(ux, s.nx, fmaf(uy, s.ny, uz * s.nz));
+        if (m.kind == 1u) {  // metal material.zig:59-65
+            cn.add(ST_SC_METAL);
+            const float rx = fmaf(-2.0f * udn, s.nx, ux), ry = fmaf(-2.0f * udn, s.ny, uy), rz = fmaf(-2.0f * udn, s.nz, uz);
+            ndx = rx; ndy = ry; ndz = rz;
+            if (m.param > 0.0f) {
+                const float3 b = sample_unit_ball(u01_24(rn.x), u01_24(rn.y), u01_24(rn.z));
+                ndx = fmaf(m.param, b.x, rx); ndy = fmaf(m.param, b.y, ry); ndz = fmaf(m.param, b.z, rz);
+            }
+            beta.x *= m.r; beta.y *= m.g; beta.z *= m.b;
+            // absorbed iff the UN-fuzzed reflection points into the surface (material.zig:64)
+            if (!(fmaf(rx, s.nx, fmaf(ry, s.ny, rz * s.nz)) > 0.0f)) return false;
+        } else {  // dielectric material.zig:72-85
+            cn.add(ST_SC_DIELECTRIC);
+            const float ratio = s.front_face ? 1.0f / m.param : m.param;
+            const float cos_theta = fminf(-udn, 1.0f);
+            const float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+            const bool can_refract = ratio * sin_theta <= 1.0f;
+            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            r0 *= r0;
+            const float om = 1.0f - cos_theta, om2 = om * om;
+            const float refl = fmaf(1.0f - r0, om2 * om2 * om, r0);  // Schlick material.zig:87-91
+            if (can_refract && refl < u01_24(rn.x)) {  // refract material.zig:116-121
+                const float px = ratio * fmaf(cos_theta, s.nx, ux), py = ratio * fmaf(cos_theta, s.ny, uy),
+                            pz = ratio * fmaf(cos_theta, s.nz, uz);
+                const float par = -sqrtf(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
+                ndx = fmaf(par, s.nx, px); ndy = fmaf(par, s.ny, py); ndz = fmaf(par, s.nz, pz);
+            } else {  // reflect material.zig:112-114
+                ndx = fmaf(-2.0f * udn, s.nx, ux); ndy = fmaf(-2.0f * udn, s.ny, uy); ndz = fmaf(-2.0f * udn, s.nz, uz);
+            }
+        }
+    }
+    r.ox = s.px; r.oy = s.py; r.oz = s.pz;
+    r.dx = ndx; r.dy = ndy; r.dz = ndz;  // time is kept (material.zig:49)
+    return true;
+}
+
+}  // namespace rtw

@@ -1,0 +1,151 @@
+"""ctypes binding of csrc/ -> _build/librtw_cuda.so (the C ABI of include/rtw_cuda.h).
+
+There is no fallback of any kind: if the library is missing or no CUDA device is present every call
+raises.  Nothing in here touches oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, build
+
+_lib = None
+
+
+class RtwCudaError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return build.CUDA_LIB
+
+
+def load(build_if_missing=True):
+    """Load librtw_cuda.so (building it in-tree first if it is absent or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        build.build_cuda()
+    if not os.path.exists(build.CUDA_LIB):
+        raise RtwCudaError(f"{build.CUDA_LIB} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    L = C.CDLL(build.CUDA_LIB)
+    vp = C.c_void_p
+    u32p, dp, u8p, fp = C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    L.rtw_cuda_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.rtw_cuda_destroy.argtypes = [vp]
+    L.rtw_cuda_destroy.restype = None
+    L.rtw_cuda_last_error.argtypes = [vp]
+    L.rtw_cuda_last_error.restype = C.c_char_p
+    L.rtw_cuda_abi_version.restype = C.c_uint32
+    L.rtw_cuda_upload_scene.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    L.rtw_cuda_render.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), vp, vp]
+    L.rtw_cuda_accumulate.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), vp, vp]
+    L.rtw_cuda_resolve.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    L.rtw_cuda_resolve_multi.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    L.rtw_cuda_trace_rays.argtypes = [vp, C.c_uint32, dp, C.c_uint32, C.c_uint32, u32p, dp, dp, dp]
+    L.rtw_cuda_primary_hits.argtypes = [vp, C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        u32p, dp, dp]
+    L.rtw_cuda_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    L.rtw_cuda_measure_fp32_peak.argtypes = [vp, dp, dp]
+    for name in abi.CUDA_SYMBOLS:
+        getattr(L, name)  # AttributeError here = the .so does not export what the header declares
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    """One rtw_ctx: a CUDA device + an uploaded scene."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        self.h = C.c_void_p()
+        rc = self.L.rtw_cuda_create(device, C.byref(self.h))
+        if rc != 0:
+            raise RtwCudaError(f"rtw_cuda_create({device}) -> {rc}: {self.L.rtw_cuda_last_error(None).decode()}")
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rtw_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RtwCudaError(f"{what} -> {rc}: {self.L.rtw_cuda_last_error(self.h).decode()}")
+
+    def upload_scene(self, desc, keep=None):
+        self._check(self.L.rtw_cuda_upload_scene(self.h, C.byref(desc)), "rtw_cuda_upload_scene")
+        self._keep = keep
+
+    @staticmethod
+    def params(width, height, spp_begin, spp_end, spp_total=0, max_depth=50, variant=abi.VARIANT_AUTO, flags=0,
+               seed=42, background=(0.7, 0.8, 1.0)):
+        p = abi.RenderParams(width=width, height=height, spp_begin=spp_begin, spp_end=spp_end, spp_total=spp_total,
+                             max_depth=max_depth, variant=variant, flags=flags, seed=seed)
+        p.background[:] = [float(x) for x in background]
+        return p
+
+    def render(self, cam, params, want_accum=False, rgb8=None, accum=None):
+        """Host-buffer render (the drop-in call).  Returns (rgb8[H,W,3] top row first, accum[H,W,4] or None)."""
+        H, W = params.height, params.width
+        if rgb8 is None:
+            rgb8 = np.empty((H, W, 3), dtype=np.uint8)
+        if want_accum and accum is None:
+            accum = np.empty((H, W, 4), dtype=np.float32)
+        self._check(self.L.rtw_cuda_render(self.h, C.byref(cam), C.byref(params), rgb8.ctypes.data,
+                                           accum.ctypes.data if accum is not None else None), "rtw_cuda_render")
+        return rgb8, accum
+
+    def accumulate(self, cam, params, d_accum_ptr, stream=None):
+        self._check(self.L.rtw_cuda_accumulate(self.h, C.byref(cam), C.byref(params), d_accum_ptr, stream),
+                    "rtw_cuda_accumulate")
+
+    def resolve(self, d_accum_ptr, width, height, spp_total, d_rgb8_ptr, stream=None):
+        self._check(self.L.rtw_cuda_resolve(self.h, d_accum_ptr, width, height, spp_total, d_rgb8_ptr, stream),
+                    "rtw_cuda_resolve")
+
+    def resolve_multi(self, d_accum_ptrs, width, height, spp_total, d_rgb8_ptr, stream=None):
+        arr = (C.c_void_p * len(d_accum_ptrs))(*d_accum_ptrs)
+        self._check(self.L.rtw_cuda_resolve_multi(self.h, arr, len(d_accum_ptrs), width, height, spp_total,
+                                                  d_rgb8_ptr, stream), "rtw_cuda_resolve_multi")
+
+    def trace_rays(self, rays, precision=32, variant=abi.VARIANT_AUTO):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        n = rays.shape[0]
+        ids = np.zeros(n, dtype=np.uint32)
+        t, nrm, uv = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 2))
+        self._check(self.L.rtw_cuda_trace_rays(self.h, n, _dp(rays), precision, variant,
+                                               ids.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(t), _dp(nrm), _dp(uv)),
+                    "rtw_cuda_trace_rays")
+        return ids, t, nrm, uv
+
+    def primary_hits(self, cam, width, height, precision=32, variant=abi.VARIANT_AUTO):
+        ids = np.zeros((height, width), dtype=np.uint32)
+        t, nrm = np.zeros((height, width)), np.zeros((height, width, 3))
+        self._check(self.L.rtw_cuda_primary_hits(self.h, C.byref(cam), width, height, precision, variant,
+                                                 ids.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(t), _dp(nrm)),
+                    "rtw_cuda_primary_hits")
+        return ids, t, nrm
+
+    def stats(self):
+        s = abi.Stats()
+        self._check(self.L.rtw_cuda_stats(self.h, C.byref(s)), "rtw_cuda_stats")
+        return s.as_dict()
+
+    def measure_fp32_peak(self):
+        tf, mhz = C.c_double(0), C.c_double(0)
+        self._check(self.L.rtw_cuda_measure_fp32_peak(self.h, C.byref(tf), C.byref(mhz)), "rtw_cuda_measure_fp32_peak")
+        return tf.value, mhz.value
