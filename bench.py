@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the path-tracing hot path (BASELINE.json metric: Mpaths/s & Mrays/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one full frame: every pixel of the 1920x1080 random-spheres scene (the reference's scene 1,
+src/main.zig:157-221, camera main.zig:320-326 at 16:9), 500 samples per pixel PER GPU, depth 50
+(BASELINE.json configs[1]).  With N > 1 ranks (one process per GPU, torchrun) rank r traces sample indices
+[500 r, 500 (r+1)) of every pixel into its own fp32 buffer, one NCCL reduce sums the buffers onto rank 0, rank 0
+resolves: weak scaling (per-GPU work fixed), the spp-split data path of SURVEY §8(e).
+
+`value`   device-timed whole-job Mpaths/s, inputs resident in HBM (CUDA events on the launching stream, max over
+          ranks, L2 flushed between iterations).
+`e2e`     the same metric through the host-buffer C-ABI call (rtw_cuda_upload_scene + rtw_cuda_render with HOST
+          buffers: scene tables and camera go host->device, the u8 image comes device->host, every step).
+`roofline` FP32-pipe roofline of the path-tracing kernel: counted algorithmic flops (event counters of an
+          instrumented replay x the per-event constants of SURVEY §8d) / kernel time, against the FFMA peak measured
+          on this device in this run.
+`cpu_baseline` the oracle port (f64 restatement of the reference, linear scan) on the box's host cores, on a
+          bounded sample of the same frame.
+
+--impl reference: the reference's own CPU algorithm (the oracle port; the Zig build cannot be produced in this
+image) on all host threads, same config/metric.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, SPP, DEPTH, SEED, GRID = 1920, 1080, 500, 50, 42, 3
+
+# algorithmic flops per event (FMA = 2)
+FLOPS = dict(paths=45, rays=3 + 9, node_tests=25, sphere_tests=23, sphere_roots=6, moving_tests=12, sphere_finalise=26,
+             rect_tests=2, rect_accepts=18, xform_apps=30, scatter_diffuse=40, scatter_metal=55, scatter_dielectric=60,
+             tex_checker=8, tex_image=8)
+
+
+def counted_flops(st):
+    return float(sum(st[k] * v for k, v in FLOPS.items()))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path (oracle port), all host threads, same config."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rtw_b200
+    import oracle_binding as ob
+    hs = rtw_b200.HostScene(1, grid=GRID, seed=SEED)
+    osc = ob.OracleScene.from_desc(hs.desc, keep=hs)
+    cam = hs.camera(aspect=WIDTH / HEIGHT)
+    nt = ob.num_threads()
+    spp_step = 4  # bounded sample of the 500-spp frame: cost is exactly linear in spp
+    for _ in range(args.warmup):
+        osc.render(cam, WIDTH, HEIGHT, 1, DEPTH, hs.background, seed=1, precision=64, nthreads=nt, want_rgb8=False)
+    secs, paths, rays = 0.0, 0, 0
+    for k in range(args.steps):
+        r = osc.render(cam, WIDTH, HEIGHT, spp_step, DEPTH, hs.background, seed=100 + k, precision=64, nthreads=nt)
+        secs += r["secs"]; paths += r["paths"]; rays += r["rays"]
+    val = paths / secs / 1e6
+    sample = f"{WIDTH}x{HEIGHT} x {spp_step} spp per step (of {SPP}); f64 oracle port, linear scan, OpenMP over scanlines"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpaths/s", "value": val, "unit": "Mpaths/s", "mrays_per_s": rays / secs / 1e6,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.gpus), "gpu_launches": 0,
+        "cpu_baseline": {"value": val, "unit": "Mpaths/s", "cores": nt, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def config_dict(n_gpus):
+    return {"workload": f"reference scene 1 (random spheres, grid half-extent {GRID}, <=40 prims, checker ground, moving "
+                        f"diffuse spheres) {WIDTH}x{HEIGHT}, {SPP} spp per GPU, depth {DEPTH} = BASELINE.json configs[1]",
+            "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_total": SPP * n_gpus, "max_depth": DEPTH,
+            "seed": SEED, "partition": f"spp split x{n_gpus} + NCCL reduce to rank 0" if n_gpus > 1 else "single GPU",
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rtw_b200
+    from rtw_b200 import abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    spp = args.spp
+    ctx = rtw_b200.Context(local_rank)
+    hs = rtw_b200.HostScene(1, grid=GRID, seed=SEED)
+    cam = hs.camera(aspect=WIDTH / HEIGHT)
+    ctx.upload_scene(hs.desc, keep=hs)
+    lo, hi = rtw_b200.dist.spp_range(rank, world, spp * world)
+    spp_total = spp * world
+
+    accum = torch.zeros(HEIGHT, WIDTH, 4, dtype=torch.float32, device="cuda")
+    rgb8 = torch.zeros(HEIGHT, WIDTH, 3, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    params = ctx.params(WIDTH, HEIGHT, lo, hi, spp_total, DEPTH, args.variant, 0, SEED, hs.background)
+
+    def step():
+        accum.zero_()
+        ctx.accumulate(cam, params, accum.data_ptr(), stream)
+        if world > 1:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            ctx.resolve(accum.data_ptr(), WIDTH, HEIGHT, spp_total, rgb8.data_ptr(), stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    sync_all()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush, outside the timed events
+        ev[k][0].record()
+        accum.zero_()
+        ctx.accumulate(cam, params, accum.data_ptr(), stream)
+        ev[k][2].record()
+        if world > 1:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            ctx.resolve(accum.data_ptr(), WIDTH, HEIGHT, spp_total, rgb8.data_ptr(), stream)
+        ev[k][1].record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(a.elapsed_time(b) for a, b, _ in ev)
+    ms_kernel = sum(a.elapsed_time(c) for a, _, c in ev)  # zero + path-tracing kernel
+    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_kernel = float(t[0]), float(t[1])
+    paths_step = WIDTH * HEIGHT * spp * world
+    value = paths_step * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- e2e: the host-buffer C-ABI call, H2D + D2H inside the timed region ----------------------------------
+    host_img = torch.empty(HEIGHT, WIDTH, 3, dtype=torch.uint8).pin_memory()
+    host_np = host_img.numpy()
+    scene_bytes = (hs.desc.n_prims * ctypes.sizeof(abi.Prim) + hs.desc.n_materials * ctypes.sizeof(abi.Material)
+                   + hs.desc.n_textures * ctypes.sizeof(abi.Texture) + hs.desc.n_xforms * ctypes.sizeof(abi.Xform))
+    h2d = scene_bytes + ctypes.sizeof(abi.Camera) + ctypes.sizeof(abi.RenderParams)
+    d2h = HEIGHT * WIDTH * 3
+    e2e_steps = max(2, min(args.steps, 3))
+
+    def e2e_step():
+        ctx.upload_scene(hs.desc, keep=hs)
+        if world == 1:
+            ctx.render(cam, params, rgb8=host_np)  # blocking; copies the image into pinned host memory
+        else:
+            step()
+            if rank == 0:
+                host_img.copy_(rgb8, non_blocking=True)
+            torch.cuda.synchronize()
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_secs = time.perf_counter() - t0
+    te = torch.tensor([e2e_secs], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = paths_step * e2e_steps / float(te[0]) / 1e6
+
+    # ---- roofline: replay one step with event counters on (same Philox keys => same paths) -------------------
+    pstat = ctx.params(WIDTH, HEIGHT, lo, hi, spp_total, DEPTH, args.variant, abi.FLAG_COUNT_EVENTS, SEED, hs.background)
+    ctx.render(cam, pstat, rgb8=host_np)
+    st = ctx.stats()
+    sums = torch.tensor([float(st["rays"]), float(st["paths"]), counted_flops(st)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    rays_step, flops_step = float(sums[0]), float(sums[2])
+
+    if rank == 0:
+        peak_tf, peak_mhz = ctx.measure_fp32_peak()
+        kernel_ms = ms_kernel / args.steps
+        achieved = counted_flops(st) / (kernel_ms * 1e-3) / 1e12  # rank 0's kernel, rank 0's flops
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "mrays_per_s": rays_step * args.steps / (ms_total * 1e-3) / 1e6,
+            "rays_per_path": rays_step / paths_step, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "call": "rtw_cuda_upload_scene + rtw_cuda_render (host buffers)" if world == 1
+                    else "upload + accumulate + NCCL reduce + resolve + D2H image"},
+            "gpu_launches": 2 * args.steps,
+            "kernel": {"name": "k_megakernel", "variant": st["variant_used"], "ms_per_launch": kernel_ms,
+                       "flops_per_ray_counted": counted_flops(st) / max(1, st["rays"])},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": traffic, "peak_source": f"FFMA microbenchmark measured in this run on this device ({peak_mhz:.0f} MHz max clock)",
+                         "note": "FP32-pipe roofline (north_star: not a dense contraction, no tensor cores; HBM traffic is one 33 MB accumulation buffer per frame)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_binding as ob
+            osc = ob.OracleScene.from_desc(hs.desc, keep=hs)
+            nt = ob.num_threads()
+            cspp = 12
+            r = osc.render(cam, WIDTH, HEIGHT, cspp, DEPTH, hs.background, seed=5, precision=64, nthreads=nt, want_rgb8=False)
+            r1 = osc.render(cam, WIDTH // 4, HEIGHT // 4, 8, DEPTH, hs.background, seed=5, precision=64, nthreads=1,
+                            continue_stream=False, want_rgb8=False)
+            line["cpu_baseline"] = {
+                "value": r["paths"] / r["secs"] / 1e6, "unit": "Mpaths/s", "cores": nt, "kind": "port",
+                "mrays_per_s": r["rays"] / r["secs"] / 1e6,
+                "sample": f"{WIDTH}x{HEIGHT} x {cspp} spp of the {SPP}-spp frame ({r['secs']:.1f} s wall on {nt} threads); f64 oracle port, linear scan",
+                "value_1_thread": r1["paths"] / r1["secs"] / 1e6,
+                "sample_1_thread": f"{WIDTH // 4}x{HEIGHT // 4} x 8 spp, single sequential stream as the reference ({r1['secs']:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,7 @@ class OracleScene:
     def export(self):
         d = _abi().SceneDesc()
         lib().orc_scene_export(self.h, C.byref(d))
+        d._owner = self  # the pointers live as long as the oracle scene
         return d
 
     def config(self):

@@ -1,0 +1,378 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (north_star: "hit ids and hit/miss masks bit-exact, a stated tolerance only on t/normal; converged
+images within a stated RMSE tolerance because the RNG streams differ"):
+  * reference-order probes (precision 32 / 64): prim ids, hit/miss mask, t AND normal bit-identical to the
+    oracle evaluated at the same precision (both sides: no FMA contraction, IEEE div/sqrt);
+  * production arithmetic (precision 0: robust fp32 sphere form, FMA on) against the f64 oracle: id mismatches
+    <= 5e-4 of pixels (silhouettes / edges only), |dt| <= 2e-3 * max(1,|t|), |dn|_inf <= 2e-3 on agreeing pixels;
+  * images: per-channel mean within 0.5 % of a 16x-spp oracle render (bias gate), and
+    RMSE(GPU_N, ref) <= 1.25 * RMSE(oracle_N, ref) (noise gate).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import scene_util
+
+pytestmark = pytest.mark.gpu
+MISS = 0xFFFFFFFF
+
+
+def _scene(rtw, oracle, sid, grid=3):
+    hs = rtw.HostScene(sid, grid=grid)
+    return hs, oracle.OracleScene.from_desc(hs.desc, keep=hs)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primary hits
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sid,grid,W,H", [(1, 3, 600, 400), (1, 11, 480, 270), (2, 3, 300, 200), (3, 3, 150, 100),
+                                          (4, 3, 300, 200), (5, 3, 300, 200), (6, 3, 600, 600), (7, 3, 480, 270)])
+@pytest.mark.parametrize("precision", [32, 64])
+def test_primary_hits_bit_exact(rtw, oracle, ctx, sid, grid, W, H, precision):
+    hs, osc = _scene(rtw, oracle, sid, grid)
+    cam = hs.camera(aspect=W / H)
+    ctx.upload_scene(hs.desc, keep=hs)
+    oid, ot, on = osc.primary_hits(cam, W, H, precision)
+    assert 0 < (oid == MISS).sum() < oid.size or sid == 6
+    for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+        gid, gt, gn = ctx.primary_hits(cam, W, H, precision, variant)
+        assert np.array_equal(gid, oid), f"{(gid != oid).sum()} id mismatches"
+        assert np.array_equal(gt, ot), "t differs in bits"
+        assert np.array_equal(gn, on), "normal differs in bits"
+
+
+@pytest.mark.parametrize("sid,grid,W,H", [(1, 3, 600, 400), (1, 11, 600, 400), (2, 3, 300, 200), (4, 3, 300, 200),
+                                          (5, 3, 300, 200), (6, 3, 600, 600), (7, 3, 480, 270)])
+def test_production_primary_hits_vs_f64_oracle(rtw, oracle, ctx, sid, grid, W, H):
+    hs, osc = _scene(rtw, oracle, sid, grid)
+    cam = hs.camera(aspect=W / H)
+    ctx.upload_scene(hs.desc, keep=hs)
+    oid, ot, on = osc.primary_hits(cam, W, H, 64)
+    for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+        gid, gt, gn = ctx.primary_hits(cam, W, H, 0, variant)
+        mism = gid != oid
+        assert mism.mean() <= 5e-4, f"{mism.sum()} of {oid.size} ids differ from the f64 oracle"
+        ok = ~mism & (oid != MISS)
+        assert (np.abs(gt - ot)[ok] <= 2e-3 * np.maximum(1.0, np.abs(ot[ok]))).all()
+        assert np.abs(gn - on)[ok].max() <= 2e-3
+
+
+def test_primary_hits_at_baseline_resolution(rtw, oracle, ctx):
+    """BASELINE.json configs[1] geometry (1920x1080): fp32 reference-order ids bit-exact over all 2M pixels."""
+    hs, osc = _scene(rtw, oracle, 1)
+    cam = hs.camera(aspect=16 / 9)
+    ctx.upload_scene(hs.desc, keep=hs)
+    oid, ot, _ = osc.primary_hits(cam, 1920, 1080, 32)
+    gid, gt, _ = ctx.primary_hits(cam, 1920, 1080, 32, rtw.abi.VARIANT_MEGA_BVH)
+    assert np.array_equal(gid, oid) and np.array_equal(gt, ot)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# arbitrary rays on random scenes (moving spheres, rects, instanced boxes), BVH == linear scan
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_trace_rays_random_scene(rtw, oracle, ctx, seed):
+    rng = np.random.default_rng(seed)
+    desc = scene_util.random_scene(rng)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    ctx.upload_scene(desc, keep=desc)
+    rays = scene_util.random_rays(rng, 50000)
+    for precision in (32, 64):
+        oid, ot, on, ouv = osc.trace_rays(rays, precision)
+        assert 0.2 < (oid != MISS).mean() < 1.0
+        for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+            gid, gt, gn, guv = ctx.trace_rays(rays, precision, variant)
+            assert np.array_equal(gid, oid) and np.array_equal(gt, ot) and np.array_equal(gn, on)
+            # u,v come from atan2/acos (libm vs CUDA libm): tolerance, not bits (seam u=0 == u=1)
+            du = np.abs(guv[:, 0] - ouv[:, 0])
+            du = np.minimum(du, 1.0 - du)
+            assert du.max() <= (1e-5 if precision == 32 else 1e-12) and np.abs(guv[:, 1] - ouv[:, 1]).max() <= (2e-4 if precision == 32 else 1e-7)
+    # production arithmetic: flat and BVH must agree with each other exactly, and with f64 almost everywhere
+    a = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_FLAT)
+    b = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_BVH)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    oid = osc.trace_rays(rays, 64)[0]
+    assert (a[0] != oid).mean() <= 1e-3
+
+
+def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx):
+    """10^4-sphere field (config C4's generator at grid 50): device BVH == device linear scan == oracle."""
+    hs = rtw.HostScene(rtw.host_lib.SCENE_SPHERE_FIELD, grid=50)
+    osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
+    ctx.upload_scene(hs.desc, keep=hs)
+    rng = np.random.default_rng(11)
+    n = 20000
+    rays = np.zeros((n, 7))
+    rays[:, 0:3] = rng.uniform(-40, 40, (n, 3)) * [1, 0.05, 1] + [0, 5, 0]
+    rays[:, 3:6] = rng.normal(size=(n, 3)) * [1, 0.3, 1]
+    rays[:, 6] = rng.uniform(0, 1, n)
+    oid, ot, _, _ = osc.trace_rays(rays, 32, use_bvh=True)
+    flat = ctx.trace_rays(rays, 32, rtw.abi.VARIANT_MEGA_FLAT)
+    bvh = ctx.trace_rays(rays, 32, rtw.abi.VARIANT_MEGA_BVH)
+    assert np.array_equal(flat[0], bvh[0]) and np.array_equal(flat[1], bvh[1])
+    assert np.array_equal(bvh[0], oid) and np.array_equal(bvh[1], ot)
+    assert ctx.stats()["bvh_depth"] <= 64
+
+
+def test_ties_later_element_wins(rtw, oracle, ctx):
+    """Two coincident rects: the reference's scan keeps the later one (hittable.zig:235-242, t_max inclusive)."""
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    for _ in range(3):
+        b.rect(rtw.abi.PRIM_XY_RECT, -1, 1, -1, 1, 0.0, m)
+    b.sphere((5, 0, 0), 1.0, m)
+    b.sphere((5, 0, 0), 1.0, m)
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    rays = np.array([[0.1, 0.2, 3, 0, 0, -1, 0], [5, 0, 4, 0, 0, -1, 0.5]], dtype=np.float64)
+    for precision in (32, 64, 0):
+        for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+            ids = ctx.trace_rays(rays, precision, variant)[0]
+            assert ids.tolist() == [2, 4], (precision, variant, ids)
+    assert osc.trace_rays(rays, 64)[0].tolist() == [2, 4]
+
+
+def test_edge_cases(rtw, oracle, ctx):
+    # empty scene: everything misses, the image is the background (resolve KAT: (.7,.8,1) -> 214,228,255)
+    b = scene_util.DescBuilder()
+    b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    cam = rtw.camera_init((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.1)
+    ids = ctx.primary_hits(cam, 33, 17, 32)[0]
+    assert (ids == MISS).all()
+    for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+        rgb, acc = ctx.render(cam, ctx.params(33, 17, 0, 5, 5, 50, variant), want_accum=True)
+        assert (rgb == np.array([214, 228, 255], dtype=np.uint8)).all()
+        assert (acc[..., 3] == 5).all()
+    # ragged image sizes (not multiples of the 8x4 tile), 1x1, zero samples
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    for W, H in ((1, 1), (7, 3), (9, 5), (64, 1), (1, 33)):
+        rgb, acc = ctx.render(hs.camera(), ctx.params(W, H, 0, 3, 3), want_accum=True)
+        assert rgb.shape == (H, W, 3) and (acc[..., 3] == 3).all() and np.isfinite(acc).all()
+    rgb, acc = ctx.render(hs.camera(), ctx.params(8, 8, 4, 4, 4), want_accum=True)  # empty spp range
+    assert (acc == 0).all() and (rgb == 0).all()
+    # depth limit: max_depth = 1 -> only background / emitted light survives one bounce deep paths (main.zig:105-108)
+    rgb1, acc1 = ctx.render(hs.camera(), ctx.params(60, 40, 0, 8, 8, 1), want_accum=True)
+    assert acc1[..., :3].max() <= 8 * 1.0 + 1e-3
+    assert (acc1[20, 30, :3] == 0).all()  # centre pixel: every sample hits a sphere, scatters once, then depth runs out
+    # rays parallel to a rect plane / starting on it never hit it (t = inf or nan compares false)
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    b.rect(rtw.abi.PRIM_XZ_RECT, -1, 1, -1, 1, 0.0, m)
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    rays = np.array([[0, 0, -3, 0, 0, 1, 0], [0, 1, -3, 0, 0, 1, 0], [0, 1, 0, 0, -1, 0, 0], [0, 0, 0, 0, 1, 0, 0]], dtype=np.float64)
+    want = osc.trace_rays(rays, 64)[0]
+    for precision in (32, 64, 0):
+        for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+            assert np.array_equal(ctx.trace_rays(rays, precision, variant)[0], want), (precision, variant)
+
+
+def test_validation_errors(rtw, ctx):
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    b.sphere((0, 0, 0), 1, m)
+    desc = b.build()
+    desc.prims[0].material = 7
+    with pytest.raises(rtw.RtwCudaError, match="material 7 out of range"):
+        ctx.upload_scene(desc)
+    desc.prims[0].material = 0
+    desc.prims[0].kind = 9
+    with pytest.raises(rtw.RtwCudaError, match="bad kind"):
+        ctx.upload_scene(desc)
+    desc.prims[0].kind = 0
+    ctx.upload_scene(desc, keep=desc)
+    cam = rtw.camera_init((0, 0, 5), (0, 0, 0), (0, 1, 0), 20.0, 1.0, 0.0)
+    with pytest.raises(rtw.RtwCudaError, match="unknown variant"):
+        ctx.render(cam, ctx.params(8, 8, 0, 1, 1, 50, 17))
+    with pytest.raises(rtw.RtwCudaError, match="spp_end < spp_begin"):
+        ctx.render(cam, ctx.params(8, 8, 3, 1, 1))
+    c2 = rtw.Context(0)
+    with pytest.raises(rtw.RtwCudaError, match="no scene uploaded"):
+        c2.render(cam, ctx.params(8, 8, 0, 1, 1))
+    c2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# resolve (K4) and the multi-buffer reduce+resolve
+# ---------------------------------------------------------------------------------------------------------
+def test_resolve_kat_and_row_flip(rtw, oracle, ctx):
+    import torch
+    W, H, spp = 8, 5, 8
+    avgs = [0.0, 0.25, 0.5, 0.7, 0.8, 1.0, 4.0, float("nan")]
+    want = [0, 128, 181, 214, 228, 255, 255, 0]   # SURVEY App. C; NaN -> 0 (App. B Q16)
+    acc = torch.zeros(H, W, 4, device="cuda")
+    for i, a in enumerate(avgs):
+        acc[:, i, 0] = a * spp
+        acc[:, i, 1] = a * spp
+    acc[:, :, 2] = torch.arange(H, device="cuda").float()[:, None] * spp / 16.0   # row marker in blue
+    out = torch.zeros(H, W, 3, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.resolve(acc.data_ptr(), W, H, spp, out.data_ptr())
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert o[0, :, 0].tolist() == want and o[3, :, 1].tolist() == want
+    for j in range(H):  # accumulation row j lands in image row H-1-j (main.zig:396)
+        assert o[H - 1 - j, 0, 2] == oracle.lib().orc_kat_resolve(j * spp / 16.0, spp)
+    # every representable average: GPU quantisation == oracle quantisation
+    vals = torch.linspace(0, 1.2, 4096, device="cuda")
+    acc = torch.zeros(1, 4096, 4, device="cuda")
+    acc[0, :, 0] = vals * 3
+    out = torch.zeros(1, 4096, 3, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.resolve(acc.data_ptr(), 4096, 1, 3, out.data_ptr())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()[0, :, 0]
+    sums = acc[0, :, 0].cpu().numpy().astype(np.float64)
+    ref = np.array([oracle.lib().orc_kat_resolve(float(s), 3) for s in sums])
+    assert (np.abs(got.astype(int) - ref.astype(int)) <= 1).all() and (got != ref).mean() < 0.01  # fp32 vs f64 sqrt at bin edges
+
+
+def test_resolve_multi_sums_buffers(rtw, ctx):
+    import torch
+    W, H = 64, 32
+    g = torch.Generator(device="cuda").manual_seed(1)
+    bufs = [torch.rand(H, W, 4, device="cuda", generator=g) * 10 for _ in range(4)]
+    one = torch.zeros(H, W, 3, dtype=torch.uint8, device="cuda")
+    multi = torch.zeros_like(one)
+    total = bufs[0] + bufs[1] + bufs[2] + bufs[3]
+    torch.cuda.synchronize()
+    ctx.resolve(total.data_ptr(), W, H, 40, one.data_ptr())
+    ctx.resolve_multi([b.data_ptr() for b in bufs], W, H, 40, multi.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(one, multi)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# rendered images: statistical parity with the f64 oracle
+# ---------------------------------------------------------------------------------------------------------
+def _image_gates(rtw, oracle, ctx, hs, osc, W, H, spp, variant, ref_mult=16):
+    cam = hs.camera(aspect=W / H)
+    nt = oracle.num_threads()
+    ref = osc.render(cam, W, H, spp * ref_mult, hs.max_depth, hs.background, seed=1001, precision=64, nthreads=max(2, nt))
+    cpu = osc.render(cam, W, H, spp, hs.max_depth, hs.background, seed=2002, precision=64, nthreads=max(2, nt))
+    ref_img = ref["accum"] / (spp * ref_mult)
+    cpu_img = cpu["accum"] / spp
+    p = ctx.params(W, H, 0, spp, spp, hs.max_depth, variant, rtw.abi.FLAG_COUNT_EVENTS, 42, hs.background)
+    rgb, acc = ctx.render(cam, p, want_accum=True)
+    st = ctx.stats()
+    gpu_img = acc[..., :3].astype(np.float64) / spp
+    assert np.isfinite(gpu_img).all() and st["nan_pixels"] == 0
+    # gate 1: bias
+    gm, rm = gpu_img.mean(axis=(0, 1)), ref_img.mean(axis=(0, 1))
+    rel = np.abs(gm - rm) / rm
+    # gate 2: noise
+    rmse_gpu = np.sqrt(((gpu_img - ref_img) ** 2).mean())
+    rmse_cpu = np.sqrt(((cpu_img - ref_img) ** 2).mean())
+    rays_per_path_gpu = st["rays"] / st["paths"]
+    rays_per_path_cpu = cpu["rays"] / cpu["paths"]
+    return rel, rmse_gpu, rmse_cpu, rays_per_path_gpu, rays_per_path_cpu, rgb, cpu["rgb8"]
+
+
+@pytest.mark.parametrize("sid,grid,W,H,spp", [(1, 3, 240, 160, 256), (1, 11, 240, 160, 128), (2, 3, 120, 80, 256),
+                                              (3, 3, 120, 80, 128), (4, 3, 120, 80, 256), (5, 3, 120, 80, 512),
+                                              (6, 3, 100, 100, 1024), (7, 3, 160, 90, 256)])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_image_parity(rtw, oracle, ctx, sid, grid, W, H, spp, variant):
+    hs, osc = _scene(rtw, oracle, sid, grid)
+    ctx.upload_scene(hs.desc, keep=hs)
+    rel, rmse_gpu, rmse_cpu, rpp_g, rpp_c, rgb, cpu_rgb = _image_gates(rtw, oracle, ctx, hs, osc, W, H, spp, variant)
+    # Monte-Carlo noise of the two means themselves: allow it on top of the 0.5 % bias gate for the emissive
+    # scenes whose per-pixel variance is huge (Cornell light = 15, main.zig:270)
+    tol = 0.005 if sid not in (5, 6) else 0.015
+    assert (rel <= tol).all(), f"bias {rel} (rays/path gpu {rpp_g:.3f} cpu {rpp_c:.3f})"
+    assert rmse_gpu <= 1.25 * rmse_cpu, f"rmse gpu {rmse_gpu:.5f} cpu {rmse_cpu:.5f}"
+    assert abs(rpp_g - rpp_c) / rpp_c < 0.02
+    mse8 = ((rgb.astype(np.float64) - cpu_rgb.astype(np.float64)) ** 2).mean()
+    psnr = 10 * np.log10(255.0 ** 2 / max(mse8, 1e-12))
+    assert psnr > 10.0
+
+
+def test_flat_and_bvh_render_the_same_paths(rtw, ctx, monkeypatch):
+    """Identical Philox keys + identical closest hits => identical per-sample radiance; with one chunk the
+    summation order is fixed too, so the two traversal variants must agree bit for bit."""
+    monkeypatch.setenv("RTW_SPP_CHUNK", "0")
+    hs = rtw.HostScene(1, grid=11)
+    ctx.upload_scene(hs.desc, keep=hs)
+    cam = hs.camera()
+    a = ctx.render(cam, ctx.params(150, 100, 0, 16, 16, 50, 1, 0, 9, hs.background), want_accum=True)[1]
+    b = ctx.render(cam, ctx.params(150, 100, 0, 16, 16, 50, 2, 0, 9, hs.background), want_accum=True)[1]
+    assert np.array_equal(a, b)
+    c = ctx.render(cam, ctx.params(150, 100, 0, 16, 16, 50, 2, 0, 10, hs.background), want_accum=True)[1]
+    assert not np.array_equal(a, c)  # a different seed gives different samples
+
+
+def test_spp_split_equals_full_render(rtw, ctx, monkeypatch):
+    """The multi-GPU partition: sample ranges rendered separately and summed == the full range
+    (Philox is keyed by the absolute sample index).  Only fp32 summation order differs."""
+    import torch
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    cam = hs.camera()
+    W, H, spp = 200, 120, 37
+    full = ctx.render(cam, ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, hs.background), want_accum=True)
+    parts = [torch.zeros(H, W, 4, device="cuda") for _ in range(4)]
+    bounds = [0, 10, 19, 28, 37]
+    for k in range(4):
+        ctx.accumulate(cam, ctx.params(W, H, bounds[k], bounds[k + 1], spp, 50, 0, 0, 42, hs.background), parts[k].data_ptr())
+    torch.cuda.synchronize()
+    total = (parts[0] + parts[1] + parts[2] + parts[3]).cpu().numpy()
+    assert (total[..., 3] == spp).all()
+    np.testing.assert_allclose(total[..., :3], full[1][..., :3], rtol=2e-5, atol=1e-5)
+    out = torch.zeros(H, W, 3, dtype=torch.uint8, device="cuda")
+    ctx.resolve_multi([p.data_ptr() for p in parts], W, H, spp, out.data_ptr())
+    torch.cuda.synchronize()
+    diff = np.abs(out.cpu().numpy().astype(int) - full[0].astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    # chunked (atomic) and unchunked accumulation agree to fp32 rounding
+    monkeypatch.setenv("RTW_SPP_CHUNK", "5")
+    chunked = ctx.render(cam, ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, hs.background), want_accum=True)
+    np.testing.assert_allclose(chunked[1][..., :3], full[1][..., :3], rtol=2e-5, atol=1e-5)
+    assert (chunked[1][..., 3] == spp).all()
+
+
+def test_baseline_size_properties(rtw, ctx):
+    """Size-independent properties at BASELINE.json's full frame sizes (1920x1080 and 3840x2160)."""
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    cam = hs.camera(aspect=16 / 9)
+    for W, H, spp in ((1920, 1080, 4), (3840, 2160, 2)):
+        p = ctx.params(W, H, 0, spp, spp, 50, 0, rtw.abi.FLAG_COUNT_EVENTS, 42, hs.background)
+        rgb, acc = ctx.render(cam, p, want_accum=True)
+        st = ctx.stats()
+        assert st["paths"] == W * H * spp and st["rays"] >= st["paths"] and st["rays"] <= 50 * st["paths"]
+        assert (acc[..., 3] == spp).all() and np.isfinite(acc).all()
+        # energy bound: no emitters, albedo <= 1 -> radiance never exceeds the brightest background channel
+        assert acc[..., :3].max() <= spp * 1.0 + 1e-3 and acc.min() >= 0.0
+        # top rows are sky: exactly the background, quantised as the KAT says
+        assert (rgb[0, :, :] == np.array([214, 228, 255], dtype=np.uint8)).all()
+        assert 2.0 < st["rays"] / st["paths"] < 3.0
+
+
+def test_white_furnace_on_device(rtw, ctx):
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    b.sphere((0, 0, 0), 1.0, m)
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    cam = rtw.camera_init((0, 0, 4), (0, 0, 0), (0, 1, 0), 20.0, 1.0, 0.0)
+    for variant in (1, 2):
+        rgb, acc = ctx.render(cam, ctx.params(32, 32, 0, 256, 256, 50, variant, 0, 1, (1.0, 1.0, 1.0)), want_accum=True)
+        img = acc[..., :3] / 256
+        assert img.max() <= 1.0 + 1e-5
+        assert abs(img[12:20, 12:20].mean() - 0.5) < 0.01
+        rgb, acc = ctx.render(cam, ctx.params(32, 32, 0, 4, 4, 50, variant, 0, 1, (0.0, 0.0, 0.0)), want_accum=True)
+        assert acc[..., :3].max() == 0.0
+
+
+def test_fp32_peak_is_plausible(ctx):
+    tf, mhz = ctx.measure_fp32_peak()
+    assert 30.0 < tf < 100.0 and mhz > 1000
