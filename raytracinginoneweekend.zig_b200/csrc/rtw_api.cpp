@@ -248,7 +248,7 @@ DevCamera lower_camera(const rtw_camera *c) {
     return d;
 }
 
-int pick_variant(rtw_ctx *ctx, uint32_t requested, int *out) {
+int pick_variant(rtw_ctx *ctx, uint32_t requested, int *out, bool uses_smem = true) {
     int v;
     switch (requested) {
         case RTW_VARIANT_AUTO: v = ctx->n_prims <= kFlatAutoMax ? VAR_FLAT : VAR_BVH; break;
@@ -257,7 +257,7 @@ int pick_variant(rtw_ctx *ctx, uint32_t requested, int *out) {
         case RTW_VARIANT_WAVEFRONT: return fail(ctx, 1, "variant WAVEFRONT is not built yet");
         default: return fail(ctx, 1, "unknown variant %u", requested);
     }
-    if (v == VAR_FLAT && ctx->n_prims > kFlatHardMax)
+    if (v == VAR_FLAT && uses_smem && ctx->n_prims > kFlatHardMax)
         return fail(ctx, 1, "flat variant holds at most %u primitives in shared memory (scene has %u)", kFlatHardMax, ctx->n_prims);
     *out = v;
     return 0;
@@ -647,7 +647,7 @@ static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_ca
     if (precision != 0 && precision != 32 && precision != 64) return fail(ctx, 1, "precision must be 0, 32 or 64");
     if (n == 0) return 0;
     int variant = 0;
-    if (int rc = pick_variant(ctx, variant_req, &variant)) return rc;
+    if (int rc = pick_variant(ctx, variant_req, &variant, precision == 0)) return rc;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DevBuf<uint32_t> d_id;

@@ -88,9 +88,12 @@ def test_trace_rays_random_scene(rtw, oracle, ctx, seed):
             gid, gt, gn, guv = ctx.trace_rays(rays, precision, variant)
             assert np.array_equal(gid, oid) and np.array_equal(gt, ot) and np.array_equal(gn, on)
             # u,v come from atan2/acos (libm vs CUDA libm): tolerance, not bits (seam u=0 == u=1)
+            # acos(-y) is NaN when rounding leaves |y| a hair above 1 (same in the reference): same NaN mask
+            assert np.array_equal(np.isnan(guv), np.isnan(ouv))
             du = np.abs(guv[:, 0] - ouv[:, 0])
             du = np.minimum(du, 1.0 - du)
-            assert du.max() <= (1e-5 if precision == 32 else 1e-12) and np.abs(guv[:, 1] - ouv[:, 1]).max() <= (2e-4 if precision == 32 else 1e-7)
+            assert np.nanmax(du) <= (1e-5 if precision == 32 else 1e-12)
+            assert np.nanmax(np.abs(guv[:, 1] - ouv[:, 1])) <= (2e-4 if precision == 32 else 1e-7)
     # production arithmetic: flat and BVH must agree with each other exactly, and with f64 almost everywhere
     a = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_FLAT)
     b = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_BVH)
