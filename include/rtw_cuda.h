@@ -164,7 +164,10 @@ typedef struct rtw_render_params {
 } rtw_render_params;
 
 enum {
-    RTW_FLAG_COUNT_EVENTS = 1u /* run the instrumented kernel build and fill rtw_stats counters */
+    RTW_FLAG_COUNT_EVENTS = 1u, /* run the instrumented kernel build and fill rtw_stats counters */
+    RTW_FLAG_DETERMINISTIC = 2u /* lane-owns-pixel kernel: fixed fp32 summation order (bit-reproducible
+                                   frames) at some cost in lane utilisation; default is the pooled kernel
+                                   whose per-path vector atomics commute only up to fp32 rounding */
 };
 
 /* Event counters of the last render / timing of its kernels.  Event classes are the rows

@@ -10,6 +10,7 @@ MAT_DIFFUSE, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT = range(4)
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = range(4)
 VARIANT_AUTO, VARIANT_MEGA_FLAT, VARIANT_MEGA_BVH, VARIANT_WAVEFRONT = range(4)
 FLAG_COUNT_EVENTS = 1
+FLAG_DETERMINISTIC = 2
 
 
 class Prim(C.Structure):

@@ -29,7 +29,8 @@ namespace {
 constexpr double kBigSphereRadius = 64.0;
 // Scenes up to this many primitives default to the warp-uniform flat scan (measured crossover).
 constexpr uint32_t kFlatAutoMax = 64;
-constexpr uint32_t kFlatHardMax = 6144;  // 192 KB of shared memory
+constexpr uint32_t kFlatHardMax = 6000;  // the shared-memory image must stay under ~200 KB
+constexpr uint32_t kBatchSpp = 64;       // pooled kernel: a batch = one 8x4 tile x 64 samples = 2048 paths
 
 thread_local std::string g_create_error;
 
@@ -72,6 +73,7 @@ struct rtw_ctx {
     bool have_scene = false;
 
     DevBuf<DevPrim> prims_flat, prims_bvh;
+    DevBuf<float4> flat_blob;
     DevBuf<uint32_t> bvh_prim_id, prim_material;
     DevBuf<BvhNode> nodes;
     DevBuf<DevXform> xforms;
@@ -304,6 +306,7 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_images(ctx);
+    ctx->flat_blob.release();
     ctx->prims_flat.release(); ctx->prims_bvh.release(); ctx->bvh_prim_id.release(); ctx->prim_material.release();
     ctx->nodes.release(); ctx->xforms.release(); ctx->bigs.release(); ctx->materials.release(); ctx->textures.release();
     ctx->images.release(); ctx->perlins.release(); ctx->raw_prims.release(); ctx->raw_chains.release();
@@ -422,6 +425,56 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     std::vector<DevPrim> leaf_order(n);
     for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
 
+    // ---- shared-memory image for the flat scan: segmented by kind (FlatLayout) ------------------------
+    FlatLayout fl{};
+    std::vector<float4> blob;
+    {
+        std::vector<float4> sph, big, mov, rect;
+        std::vector<uint32_t> id_sph, id_big, id_mov, id_rect;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtw_prim &p = s->prims[i];
+            const DevPrim &d = flat[i];
+            if (p.kind == RTW_PRIM_SPHERE) {
+                const float4 rec = make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w);
+                uint32_t meta;
+                std::memcpy(&meta, &d.b.w, 4);
+                if (meta >> 8) { big.push_back(rec); id_big.push_back(i); }  // same order as `bigs`
+                else { sph.push_back(rec); id_sph.push_back(i); }
+            } else if (p.kind == RTW_PRIM_MOVING_SPHERE) {
+                mov.push_back(make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w));
+                mov.push_back(make_float4(d.b.x, d.b.y, d.b.z, d.a.w));
+                id_mov.push_back(i);
+            } else {
+                rect.push_back(d.a); rect.push_back(d.b);
+                id_rect.push_back(i);
+            }
+        }
+        fl.n_sphere_real = (uint32_t)(id_sph.size() + id_big.size() + id_mov.size());
+        if (id_sph.size() & 1) { sph.push_back(make_float4(0.f, 0.f, 0.f, -1.f)); id_sph.push_back(0); }
+        if (id_mov.size() & 1) { mov.push_back(make_float4(0.f, 0.f, 0.f, -1.f)); mov.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); id_mov.push_back(0); }
+        fl.n_sph = (uint32_t)id_sph.size(); fl.n_big = (uint32_t)id_big.size();
+        fl.n_mov = (uint32_t)id_mov.size(); fl.n_rect = (uint32_t)id_rect.size();
+        fl.off_sph = 0;
+        fl.off_big = fl.off_sph + (uint32_t)sph.size();
+        fl.off_mov = fl.off_big + (uint32_t)big.size();
+        fl.off_rect = fl.off_mov + (uint32_t)mov.size();
+        fl.off_ids = fl.off_rect + (uint32_t)rect.size();
+        std::vector<uint32_t> ids;
+        ids.insert(ids.end(), id_sph.begin(), id_sph.end());
+        ids.insert(ids.end(), id_big.begin(), id_big.end());
+        ids.insert(ids.end(), id_mov.begin(), id_mov.end());
+        ids.insert(ids.end(), id_rect.begin(), id_rect.end());
+        while (ids.size() & 3) ids.push_back(0);
+        blob.insert(blob.end(), sph.begin(), sph.end());
+        blob.insert(blob.end(), big.begin(), big.end());
+        blob.insert(blob.end(), mov.begin(), mov.end());
+        blob.insert(blob.end(), rect.begin(), rect.end());
+        const size_t at = blob.size();
+        blob.resize(at + ids.size() / 4);
+        if (!ids.empty()) std::memcpy(&blob[at], ids.data(), ids.size() * 4);
+        fl.total_f4 = (uint32_t)blob.size();
+    }
+
     // ---- materials / textures -------------------------------------------------------------------------
     std::vector<DevMaterial> mats(s->n_materials);
     for (uint32_t i = 0; i < s->n_materials; ++i) {
@@ -465,6 +518,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         imgs[i] = DevImage{tex, im.width, im.height, 0, 0};
     }
 
+    CK(ctx->flat_blob.upload(blob));
     CK(ctx->prims_flat.upload(flat));
     CK(ctx->prims_bvh.upload(leaf_order));
     CK(ctx->bvh_prim_id.upload(bvh.order));
@@ -480,6 +534,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     CK(ctx->raw_chains.upload(chains));
 
     DevScene &d = ctx->scene;
+    d.flat_blob = ctx->flat_blob.p; d.flat = fl;
     d.prims_flat = ctx->prims_flat.p; d.prims_bvh = ctx->prims_bvh.p; d.bvh_prim_id = ctx->bvh_prim_id.p;
     d.prim_material = ctx->prim_material.p; d.nodes = ctx->nodes.p; d.xforms = ctx->xforms.p; d.bigs = ctx->bigs.p;
     d.materials = ctx->materials.p; d.textures = ctx->textures.p; d.images = ctx->images.p; d.perlins = ctx->perlins.p;
@@ -522,37 +577,35 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     rp.tiles_x = (p->width + 7) / 8;
     rp.n_tiles = rp.tiles_x * ((p->height + 3) / 4);
 
-    const size_t smem = variant == VAR_FLAT ? (size_t)ctx->n_prims * sizeof(DevPrim) : 0;
-    const int per_sm = megakernel_ctas_per_sm(variant, stats, smem);
-    if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (smem %zu B)", smem);
+    // RTW_FLAG_DETERMINISTIC (or RTW_SPP_CHUNK=0): lane-owns-pixel kernel, one chunk, fixed summation order.
+    // Default: pooled kernel (warp-level path queue + one vector atomic per path).
+    const char *env = getenv("RTW_SPP_CHUNK");
+    const bool env_set = env && *env;
+    const bool pooled = !(p->flags & RTW_FLAG_DETERMINISTIC) && !env_set;
+    const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
+    if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (flat image %u B)", ctx->scene.flat.total_f4 * 16u);
     const int grid = per_sm * ctx->n_sms;
 
-    // Work items = tiles x sample chunks.  Enough items per resident warp that the end-of-kernel tail
-    // (warps idle while the last items finish) stays small.  RTW_SPP_CHUNK overrides (0 = one chunk:
-    // each pixel owned by one warp, deterministic summation order).
     const uint32_t spp = p->spp_end - p->spp_begin;
     uint32_t chunk = spp;
-    const char *env = getenv("RTW_SPP_CHUNK");
-    if (env && *env) {
+    if (env_set) {
         const long v = atol(env);
         chunk = v <= 0 ? spp : (uint32_t)v;
-    } else if (spp > 0) {
-        const uint64_t warps = (uint64_t)grid * 4;
-        const uint64_t want_items = warps * 48;
-        uint64_t chunks = (want_items + rp.n_tiles - 1) / rp.n_tiles;
-        chunks = std::max<uint64_t>(1, std::min<uint64_t>(chunks, spp / 16 ? spp / 16 : 1));
-        chunk = (uint32_t)((spp + chunks - 1) / chunks);
     }
     if (chunk == 0) chunk = 1;
     rp.spp_chunk = chunk;
     rp.n_chunks = spp ? (spp + chunk - 1) / chunk : 0;
+    rp.batch_spp = kBatchSpp;
+    rp.n_sblocks = (spp + kBatchSpp - 1) / kBatchSpp;
+    if ((uint64_t)rp.n_sblocks * rp.n_tiles > 0xFFFFFFF0ull) return fail(ctx, 1, "too many path batches for one launch");
+    rp.n_batches = rp.n_sblocks * rp.n_tiles;
 
     if (spp == 0) { ctx->stats.n_launches = 0; return 0; }
     if (stats) CK(cudaMemsetAsync(ctx->stat_counters.p, 0, ST_COUNT * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned int), st));
     const DevCamera dc = lower_camera(cam);
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
-    CK(launch_megakernel(variant, stats, ctx->scene, dc, rp, grid, st));
+    CK(launch_megakernel(variant, stats, pooled, ctx->scene, dc, rp, grid, st));
     if (timed) CK(cudaEventRecord(ctx->ev[1], st));
     ctx->stats.n_launches = 1;
     ctx->stats.variant_used = variant == VAR_FLAT ? RTW_VARIANT_MEGA_FLAT : RTW_VARIANT_MEGA_BVH;

@@ -72,7 +72,25 @@ struct DevPerlin {
     uint8_t perm[3][256];
 };
 
+// Shared-memory image of a small scene for the flat scan, as one blob of float4 (offsets in float4
+// units).  Primitives are SEGMENTED BY KIND so each scan loop is branch-free and unrollable:
+//   sph : static spheres        1 x float4 (cx, cy, cz, r^2)            count padded to even
+//   big : big static spheres    1 x float4 (cx, cy, cz, r^2), DevBigSphere i in scene.bigs
+//   mov : moving spheres        2 x float4 (cbx, cby, cbz, r^2), (vx, vy, vz, r)   padded to even
+//   rect: rects                 2 x float4 as DevPrim
+//   ids : uint32 prim id per entry, in the order sph | big | mov | rect
+// Padding entries have r^2 = -1 (never hit).
+struct FlatLayout {
+    uint32_t n_sph, n_big, n_mov, n_rect;  // loop trip counts (padded)
+    uint32_t off_sph, off_big, off_mov, off_rect, off_ids;
+    uint32_t total_f4;
+    uint32_t n_sphere_real;  // for the event counters
+    uint32_t pad;
+};
+
 struct DevScene {
+    const float4 *flat_blob;      // FlatLayout image, staged into shared memory by the flat kernels
+    FlatLayout flat;
     const DevPrim *prims_flat;    // reference order: slot == prim id
     const DevPrim *prims_bvh;     // BVH leaf order
     const uint32_t *bvh_prim_id;  // slot -> prim id
@@ -112,7 +130,8 @@ struct DevRender {
     uint32_t seed_lo, seed_hi;
     float bg_r, bg_g, bg_b;
     float4 *accum;                 // width*height, row j = reference scanline j
-    unsigned int *tile_counter;    // persistent-kernel work queue
+    unsigned int *tile_counter;    // persistent-kernel work queue (tiles x chunks, or path batches)
+    uint32_t n_batches, n_sblocks, batch_spp;  // pooled kernel: batch = one tile x batch_spp samples
     unsigned long long *stats;     // ST_COUNT counters (instrumented build only)
     uint32_t n_tiles, tiles_x, spp_chunk, n_chunks;
 };

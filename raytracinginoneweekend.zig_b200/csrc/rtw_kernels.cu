@@ -22,17 +22,44 @@ namespace rtw {
 
 constexpr int kBlock = 128;  // threads per CTA
 
+// stage the FlatLayout blob into shared memory (once per CTA)
+__device__ __forceinline__ void stage_flat(const DevScene &sc, float4 *s_flat) {
+    for (uint32_t i = threadIdx.x; i < sc.flat.total_f4; i += blockDim.x) s_flat[i] = sc.flat_blob[i];
+    __syncthreads();
+}
+
+// One ray of one path: closest hit, then miss / shade.  Returns false when the path ended (its
+// radiance is then complete in L).
+template <int VARIANT, bool STATS>
+__device__ __forceinline__ bool path_step(const DevScene &sc, const DevRender &rp, const float4 *s_flat, Ray &r,
+                                          uint32_t pixel, uint32_t sample, uint32_t &bounce, float3 &beta, float3 &L,
+                                          Counters<STATS> &cn) {
+    cn.add(ST_RAYS);
+    Hit h;
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<STATS>(r, s_flat, sc.flat, sc, 0.001f, cn);
+    else h = closest_hit_bvh<STATS>(r, sc, 0.001f, cn);
+    if (h.slot == kMiss) {  // main.zig:109-112
+        L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
+        return false;
+    }
+    DevPrim prim;
+    uint32_t prim_id;
+    if (VARIANT == VAR_FLAT) { prim_id = h.slot; prim = sc.prims_flat[prim_id]; }
+    else { prim = sc.prims_bvh[h.slot]; prim_id = sc.bvh_prim_id[h.slot]; }
+    ++bounce;
+    const bool go = shade<STATS>(sc, rp, r, prim, prim_id, h.t, pixel, sample, bounce, beta, L, cn);
+    // depth exhausted: the next rayColor call returns black before intersecting (main.zig:105-108)
+    return go && bounce < rp.max_depth;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic variant: lane = pixel, every pixel's samples summed in index order by one lane.
+// ---------------------------------------------------------------------------------------------
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(kBlock) k_megakernel(const DevScene sc, const DevCamera cam, const DevRender rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DevPrim *s_prims = reinterpret_cast<DevPrim *>(smem_raw);
-    if (VARIANT == VAR_FLAT) {
-        // stage the primitive table once per CTA (reference order), 32 bytes per prim
-        const float4 *src = reinterpret_cast<const float4 *>(sc.prims_flat);
-        float4 *dst = reinterpret_cast<float4 *>(s_prims);
-        for (uint32_t i = threadIdx.x; i < sc.n_prims * 2; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-    }
+    float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
+    if (VARIANT == VAR_FLAT) stage_flat(sc, s_flat);
     Counters<STATS> cn;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t total_items = rp.n_tiles * rp.n_chunks;
@@ -56,36 +83,18 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const DevScene sc, const 
         uint32_t bounce = 0, cur_sample = 0;
         bool alive = false;
         for (;;) {
-            if (!alive) {
-                if (sample < sample_end) {
-                    cur_sample = sample++;
-                    r = camera_ray(cam, rp, pixel, i, j, cur_sample);
-                    beta = make_float3(1.0f, 1.0f, 1.0f);
-                    L = make_float3(0.0f, 0.0f, 0.0f);
-                    bounce = 0;
-                    alive = true;
-                    cn.add(ST_PATHS);
-                }
+            if (!alive && sample < sample_end) {
+                cur_sample = sample++;
+                r = camera_ray(cam, rp, pixel, i, j, cur_sample);
+                beta = make_float3(1.0f, 1.0f, 1.0f);
+                L = make_float3(0.0f, 0.0f, 0.0f);
+                bounce = 0;
+                alive = true;
+                cn.add(ST_PATHS);
             }
             if (!__any_sync(0xffffffffu, alive)) break;
             if (alive) {
-                cn.add(ST_RAYS);
-                Hit h;
-                if (VARIANT == VAR_FLAT) h = closest_hit_flat<STATS>(r, s_prims, sc.n_prims, sc, 0.001f, cn);
-                else h = closest_hit_bvh<STATS>(r, sc, 0.001f, cn);
-                if (h.slot == kMiss) {  // main.zig:109-112
-                    L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
-                    alive = false;
-                } else {
-                    DevPrim prim;
-                    uint32_t prim_id;
-                    if (VARIANT == VAR_FLAT) { prim = s_prims[h.slot]; prim_id = h.slot; }
-                    else { prim = sc.prims_bvh[h.slot]; prim_id = sc.bvh_prim_id[h.slot]; }
-                    ++bounce;
-                    alive = shade<STATS>(sc, rp, r, prim, prim_id, h.t, pixel, cur_sample, bounce, beta, L, cn);
-                    // depth exhausted: the next rayColor call returns black before intersecting (main.zig:105-108)
-                    if (bounce >= rp.max_depth) alive = false;
-                }
+                alive = path_step<VARIANT, STATS>(sc, rp, s_flat, r, pixel, cur_sample, bounce, beta, L, cn);
                 if (!alive) { sum.x += L.x; sum.y += L.y; sum.z += L.z; }
             }
         }
@@ -99,6 +108,83 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const DevScene sc, const 
             } else {
                 atomicAdd(&dst->x, sum.x); atomicAdd(&dst->y, sum.y); atomicAdd(&dst->z, sum.z); atomicAdd(&dst->w, ns);
             }
+        }
+    }
+    if (STATS) cn.flush(rp.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pooled variant (default): the warp owns a pool of path indices (a batch = one 8x4 pixel tile x
+// batch_spp samples, pulled from a global atomic queue).  Whenever lanes finish their paths they are
+// handed the next indices of the pool — ballot + popc prefix, no lane ever waits for its neighbours —
+// and a finished path is added to the frame with ONE vector reduction (red.global.add.v4.f32: r, g, b
+// and the sample count).  There is no per-tile tail; only the last batches of the launch run under-full.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float4 *addr, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(kBlock) k_megakernel_pooled(const DevScene sc, const DevCamera cam, const DevRender rp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
+    if (VARIANT == VAR_FLAT) stage_flat(sc, s_flat);
+    Counters<STATS> cn;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // warp-uniform pool state
+    uint32_t pool_next = 0, pool_end = 0, pool_tx = 0, pool_ty = 0, pool_s0 = 0;
+    bool more = true;
+
+    float3 beta = make_float3(1.0f, 1.0f, 1.0f), L = make_float3(0.0f, 0.0f, 0.0f);
+    Ray r;
+    uint32_t bounce = 0, cur_sample = 0, pixel = 0;
+    bool alive = false;
+    for (;;) {
+        // ---- hand new paths to idle lanes ----
+        for (;;) {
+            const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+            if (!need) break;
+            if (pool_next == pool_end) {
+                if (!more) break;
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(rp.tile_counter, 1u);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= rp.n_batches) { more = false; break; }
+                // sample-block-major: neighbouring warps work on neighbouring tiles
+                const uint32_t sb = b / rp.n_tiles, tile = b - sb * rp.n_tiles;
+                pool_ty = tile / rp.tiles_x; pool_tx = tile - pool_ty * rp.tiles_x;
+                pool_s0 = rp.spp_begin + sb * rp.batch_spp;
+                pool_next = 0;
+                pool_end = 32u * min(rp.batch_spp, rp.spp_end - pool_s0);
+            }
+            const uint32_t take = min((uint32_t)__popc(need), pool_end - pool_next);
+            const uint32_t rank = __popc(need & lt_mask);
+            if (!alive && rank < take) {
+                const uint32_t idx = pool_next + rank;
+                const uint32_t pl = idx & 31u;
+                const uint32_t i = pool_tx * 8 + (pl & 7), j = pool_ty * 4 + (pl >> 3);
+                if (i < rp.width && j < rp.height) {  // ragged edge tiles: the slot is consumed, no path starts
+                    pixel = j * rp.width + i;
+                    cur_sample = pool_s0 + (idx >> 5);
+                    r = camera_ray(cam, rp, pixel, i, j, cur_sample);
+                    beta = make_float3(1.0f, 1.0f, 1.0f);
+                    L = make_float3(0.0f, 0.0f, 0.0f);
+                    bounce = 0;
+                    alive = true;
+                    cn.add(ST_PATHS);
+                }
+            }
+            pool_next += take;
+        }
+        if (!__any_sync(0xffffffffu, alive)) {
+            if (!more && pool_next == pool_end) break;
+            continue;
+        }
+        if (alive) {
+            alive = path_step<VARIANT, STATS>(sc, rp, s_flat, r, pixel, cur_sample, bounce, beta, L, cn);
+            if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
         }
     }
     if (STATS) cn.flush(rp.stats);
@@ -146,20 +232,15 @@ template <int VARIANT>
 __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n, const float *__restrict__ rays,
                                                   uint32_t *prim_id, float *t_out, float *normal, float *uv) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DevPrim *s_prims = reinterpret_cast<DevPrim *>(smem_raw);
-    if (VARIANT == VAR_FLAT) {
-        const float4 *src = reinterpret_cast<const float4 *>(sc.prims_flat);
-        float4 *dst = reinterpret_cast<float4 *>(s_prims);
-        for (uint32_t i = threadIdx.x; i < sc.n_prims * 2; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-    }
+    float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
+    if (VARIANT == VAR_FLAT) stage_flat(sc, s_flat);
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     const float *q = rays + 7 * (size_t)idx;
     Ray r{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
     Counters<false> cn;
     Hit h;
-    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, s_prims, sc.n_prims, sc, 0.001f, cn);
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, s_flat, sc.flat, sc, 0.001f, cn);
     else h = closest_hit_bvh<false>(r, sc, 0.001f, cn);
     if (h.slot == kMiss) {
         prim_id[idx] = kMiss; t_out[idx] = 0.0f;
@@ -169,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     }
     DevPrim prim;
     uint32_t id;
-    if (VARIANT == VAR_FLAT) { prim = s_prims[h.slot]; id = h.slot; }
+    if (VARIANT == VAR_FLAT) { id = h.slot; prim = sc.prims_flat[id]; }
     else { prim = sc.prims_bvh[h.slot]; id = sc.bvh_prim_id[h.slot]; }
     const Surface s = finalise_hit<false>(r, prim, h.t, sc, cn);
     prim_id[idx] = id; t_out[idx] = h.t;
@@ -204,42 +285,47 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from rtw_api.cpp through rtw_kernels.h)
 // ---------------------------------------------------------------------------------------------
-template <int VARIANT, bool STATS>
+template <int VARIANT, bool STATS, bool POOLED>
 static cudaError_t launch_mega_t(const DevScene &sc, const DevCamera &cam, const DevRender &rp, int grid,
                                  size_t smem, cudaStream_t st) {
+    auto kern = POOLED ? k_megakernel_pooled<VARIANT, STATS> : k_megakernel<VARIANT, STATS>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_megakernel<VARIANT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_megakernel<VARIANT, STATS><<<grid, kBlock, smem, st>>>(sc, cam, rp);
+    kern<<<grid, kBlock, smem, st>>>(sc, cam, rp);
     return cudaGetLastError();
 }
 
-cudaError_t launch_megakernel(int variant, bool stats, const DevScene &sc, const DevCamera &cam, const DevRender &rp,
-                              int grid, cudaStream_t st) {
-    const size_t smem = variant == VAR_FLAT ? (size_t)sc.n_prims * sizeof(DevPrim) : 0;
-    if (variant == VAR_FLAT) return stats ? launch_mega_t<VAR_FLAT, true>(sc, cam, rp, grid, smem, st)
-                                          : launch_mega_t<VAR_FLAT, false>(sc, cam, rp, grid, smem, st);
-    return stats ? launch_mega_t<VAR_BVH, true>(sc, cam, rp, grid, smem, st)
-                 : launch_mega_t<VAR_BVH, false>(sc, cam, rp, grid, smem, st);
+static size_t mega_smem(int variant, const DevScene &sc) {
+    return variant == VAR_FLAT ? (size_t)sc.flat.total_f4 * sizeof(float4) : 0;
 }
 
-int megakernel_ctas_per_sm(int variant, bool stats, size_t smem) {
+cudaError_t launch_megakernel(int variant, bool stats, bool pooled, const DevScene &sc, const DevCamera &cam,
+                              const DevRender &rp, int grid, cudaStream_t st) {
+    const size_t smem = mega_smem(variant, sc);
+#define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
+    RTW_CASE(VAR_FLAT, false, false); RTW_CASE(VAR_FLAT, true, false); RTW_CASE(VAR_FLAT, false, true); RTW_CASE(VAR_FLAT, true, true);
+    RTW_CASE(VAR_BVH, false, false); RTW_CASE(VAR_BVH, true, false); RTW_CASE(VAR_BVH, false, true); RTW_CASE(VAR_BVH, true, true);
+#undef RTW_CASE
+    return cudaErrorInvalidValue;
+}
+
+template <int VARIANT, bool STATS, bool POOLED>
+static int occ_t(size_t smem) {
+    auto kern = POOLED ? k_megakernel_pooled<VARIANT, STATS> : k_megakernel<VARIANT, STATS>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int n = 0;
-    cudaError_t e;
-    if (variant == VAR_FLAT) {
-        if (smem > 48 * 1024) {
-            if (stats) cudaFuncSetAttribute(k_megakernel<VAR_FLAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            else cudaFuncSetAttribute(k_megakernel<VAR_FLAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
-        e = stats ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_FLAT, true>, kBlock, smem)
-                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_FLAT, false>, kBlock, smem);
-    } else {
-        e = stats ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_BVH, true>, kBlock, 0)
-                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_megakernel<VAR_BVH, false>, kBlock, 0);
-    }
-    return e == cudaSuccess ? n : 0;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, smem) == cudaSuccess ? n : 0;
+}
+
+int megakernel_ctas_per_sm(int variant, bool stats, bool pooled, const DevScene &sc) {
+    const size_t smem = mega_smem(variant, sc);
+#define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
+    RTW_CASE(VAR_FLAT, false, false); RTW_CASE(VAR_FLAT, true, false); RTW_CASE(VAR_FLAT, false, true); RTW_CASE(VAR_FLAT, true, true);
+    RTW_CASE(VAR_BVH, false, false); RTW_CASE(VAR_BVH, true, false); RTW_CASE(VAR_BVH, false, true); RTW_CASE(VAR_BVH, true, true);
+#undef RTW_CASE
+    return 0;
 }
 
 cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st) {
@@ -252,7 +338,7 @@ cudaError_t launch_probe(int variant, const DevScene &sc, uint32_t n, const floa
                          float *normal, float *uv, cudaStream_t st) {
     const int grid = (int)((n + kBlock - 1) / kBlock);
     if (variant == VAR_FLAT) {
-        const size_t smem = (size_t)sc.n_prims * sizeof(DevPrim);
+        const size_t smem = mega_smem(variant, sc);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_probe<VAR_FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

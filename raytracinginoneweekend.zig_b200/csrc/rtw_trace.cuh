@@ -35,6 +35,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint32_t k0, uint32_t 
 // 24-bit uniform in [0,1): exactly the fp32 lattice, never 1.0
 __device__ __forceinline__ float u01_24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT, ~1 ulp, no slow path
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, ~1 ulp, no slow path
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct Ray {
     float ox, oy, oz, dx, dy, dz, time;
 };
@@ -105,7 +116,7 @@ __device__ __forceinline__ bool sphere_test(const Ray &r, float add, float inv_a
     } else {
         c = fmaf(ocx, ocx, fmaf(ocy, ocy, fmaf(ocz, ocz, -rr)));
     }
-    const float sq = sqrtf(add * discp);
+    const float sq = sqrt_approx(add * discp);
     const float bq = -bp;
     const float q = bq + copysignf(sq, bq);
     const float t0 = __fdividef(c, q), t1 = q * inv_a;
@@ -127,7 +138,7 @@ __device__ __forceinline__ bool rect_test_os(uint32_t kind, float ox, float oy, 
     if (kind == PK_XY) { ok = oz; dk = dz; oa = ox; da = dx; ob = oy; db = dy; }
     else if (kind == PK_XZ) { ok = oy; dk = dy; oa = ox; da = dx; ob = oz; db = dz; }
     else { ok = ox; dk = dx; oa = oy; da = dy; ob = oz; db = dz; }
-    const float t = (p.b.x - ok) / dk;  // IEEE division, as hittable.zig:279
+    const float t = __fdividef(p.b.x - ok, dk);  // hittable.zig:279 (2-ulp division: production arithmetic)
     if (t < t_min || t > t_max) return false;
     const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
     if (pa < p.a.x || pa > p.a.y || pb < p.a.z || pb > p.a.w) return false;
@@ -166,25 +177,156 @@ __device__ __forceinline__ bool prim_test(const Ray &r, float add, float inv_a, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Flat scan: prims staged in shared memory in REFERENCE ORDER; every lane reads the same record
-// (smem broadcast), so the scan itself has no divergence.  Sequential scan with inclusive t_max
-// reproduces the reference's tie rule (later element wins) for free.
+// Flat scan: the scene staged in shared memory as a FlatLayout blob (segmented by primitive kind).
+// Every lane reads the same record (smem broadcast): the scan has no divergence, each loop body is
+// branch-free up to the (rare) accept path, and is unrolled by two for ILP.  Segmentation changes the
+// visiting order, so the reference's tie rule ("later list element wins", hittable.zig:235-242) is
+// applied explicitly: a candidate replaces the current hit if t < best, or t == best and its prim
+// id is larger.
 // ---------------------------------------------------------------------------------------------
+struct FlatBest {
+    float t;
+    uint32_t id;
+};
+
+__device__ __forceinline__ void flat_consider(FlatBest &b, float t, uint32_t id) {
+    if (t < b.t || b.id == kMiss || id > b.id) { b.t = t; b.id = id; }
+}
+
+// discriminant of the robust form (see sphere_test): returns disc', writes oc and bp
+__device__ __forceinline__ float sphere_disc(const Ray &r, float inv_a, float cx, float cy, float cz, float rr,
+                                             float &ocx, float &ocy, float &ocz, float &bp) {
+    ocx = r.ox - cx; ocy = r.oy - cy; ocz = r.oz - cz;
+    bp = fmaf(ocx, r.dx, fmaf(ocy, r.dy, ocz * r.dz));
+    const float k = bp * inv_a;
+    const float lx = fmaf(-k, r.dx, ocx), ly = fmaf(-k, r.dy, ocy), lz = fmaf(-k, r.dz, ocz);
+    return fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, rr)));
+}
+// roots from (c, b', disc'): nearest root in [t_min, t_max]
+__device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, float bp, float discp, float t_min,
+                                            float t_max, float &t_out) {
+    const float sq = sqrt_approx(add * discp);
+    const float bq = -bp;
+    const float q = bq + copysignf(sq, bq);
+    const float t0 = __fdividef(c, q), t1 = q * inv_a;
+    float root = fminf(t0, t1);
+    if (root < t_min || t_max < root) {
+        root = fmaxf(t0, t1);
+        if (root < t_min || t_max < root) return false;
+    }
+    if (!(root == root)) return false;
+    t_out = root;
+    return true;
+}
+
 template <bool STATS>
-__device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const DevPrim *s_prims, uint32_t n, const DevScene &sc,
+__device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const float4 *s, const FlatLayout &L, const DevScene &sc,
                                                 float t_min, Counters<STATS> &cn) {
     const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-    const float inv_a = 1.0f / add;
-    Hit h{__int_as_float(0x7f800000), kMiss};
-    for (uint32_t i = 0; i < n; ++i) {
-        const DevPrim p = s_prims[i];
-        float t;
-        if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
-            h.t = t;
-            h.slot = i;
+    const float inv_a = rcp_approx(add);
+    FlatBest best{__int_as_float(0x7f800000), kMiss};
+    const uint32_t *ids = reinterpret_cast<const uint32_t *>(s + L.off_ids);
+    cn.add(ST_SPHERE_TESTS, L.n_sphere_real);
+
+    // ---- static spheres: one LDS.128 per test ----
+    {
+        const float4 *sp = s + L.off_sph, *const se = sp + L.n_sph;
+        const uint32_t *ip = ids;
+#pragma unroll 1
+        for (; sp < se; sp += 2, ip += 2) {
+            const float4 a0 = sp[0], a1 = sp[1];
+            float o0x, o0y, o0z, b0, o1x, o1y, o1z, b1;
+            const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, o0x, o0y, o0z, b0);
+            const float d1 = sphere_disc(r, inv_a, a1.x, a1.y, a1.z, a1.w, o1x, o1y, o1z, b1);
+            if (d0 >= 0.0f) {
+                cn.add(ST_SPHERE_ROOTS);
+                const float c = fmaf(o0x, o0x, fmaf(o0y, o0y, fmaf(o0z, o0z, -a0.w)));
+                float t;
+                if (sphere_root(add, inv_a, c, b0, d0, t_min, best.t, t)) flat_consider(best, t, ip[0]);
+            }
+            if (d1 >= 0.0f) {
+                cn.add(ST_SPHERE_ROOTS);
+                const float c = fmaf(o1x, o1x, fmaf(o1y, o1y, fmaf(o1z, o1z, -a1.w)));
+                float t;
+                if (sphere_root(add, inv_a, c, b1, d1, t_min, best.t, t)) flat_consider(best, t, ip[1]);
+            }
         }
     }
-    return h;
+    // ---- big static spheres: c term about the reference point ----
+    {
+        const float4 *sp = s + L.off_big;
+        for (uint32_t i = 0; i < L.n_big; ++i) {
+            const float4 a0 = sp[i];
+            float ox, oy, oz, bp;
+            const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, ox, oy, oz, bp);
+            if (d0 >= 0.0f) {
+                cn.add(ST_SPHERE_ROOTS);
+                const DevBigSphere g = sc.bigs[i];
+                const float ax = r.ox - g.qx, ay = r.oy - g.qy, az = r.oz - g.qz;
+                const float aa = fmaf(ax, ax, fmaf(ay, ay, az * az));
+                const float am = fmaf(ax, g.mx, fmaf(ay, g.my, az * g.mz));
+                const float c = fmaf(2.0f, am, aa) + g.K;
+                float t;
+                if (sphere_root(add, inv_a, c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[L.n_sph + i]);
+            }
+        }
+    }
+    // ---- moving spheres: centre(time) = cb + vel*time (hittable.zig:219-221) ----
+    {
+        const float4 *sp = s + L.off_mov, *const se = sp + 2 * L.n_mov;
+        const uint32_t *ip = ids + L.n_sph + L.n_big;
+#pragma unroll 1
+        for (; sp < se; sp += 4, ip += 2) {
+            const float4 a0 = sp[0], v0 = sp[1], a1 = sp[2], v1 = sp[3];
+            float o0x, o0y, o0z, b0, o1x, o1y, o1z, b1;
+            const float d0 = sphere_disc(r, inv_a, fmaf(v0.x, r.time, a0.x), fmaf(v0.y, r.time, a0.y),
+                                         fmaf(v0.z, r.time, a0.z), a0.w, o0x, o0y, o0z, b0);
+            const float d1 = sphere_disc(r, inv_a, fmaf(v1.x, r.time, a1.x), fmaf(v1.y, r.time, a1.y),
+                                         fmaf(v1.z, r.time, a1.z), a1.w, o1x, o1y, o1z, b1);
+            if (d0 >= 0.0f) {
+                cn.add(ST_SPHERE_ROOTS);
+                const float c = fmaf(o0x, o0x, fmaf(o0y, o0y, fmaf(o0z, o0z, -a0.w)));
+                float t;
+                if (sphere_root(add, inv_a, c, b0, d0, t_min, best.t, t)) flat_consider(best, t, ip[0]);
+            }
+            if (d1 >= 0.0f) {
+                cn.add(ST_SPHERE_ROOTS);
+                const float c = fmaf(o1x, o1x, fmaf(o1y, o1y, fmaf(o1z, o1z, -a1.w)));
+                float t;
+                if (sphere_root(add, inv_a, c, b1, d1, t_min, best.t, t)) flat_consider(best, t, ip[1]);
+            }
+        }
+    }
+    // ---- rects: the instance transform is recomputed only when the (warp-uniform) xform id changes ----
+    {
+        const float4 *rp = s + L.off_rect;
+        const uint32_t *rid = ids + L.n_sph + L.n_big + L.n_mov;
+        int cur = -1;
+        float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+        for (uint32_t i = 0; i < L.n_rect; ++i) {
+            DevPrim p;
+            p.a = rp[2 * i]; p.b = rp[2 * i + 1];
+            cn.add(ST_RECT_TESTS);
+            const int xi = __float_as_int(p.b.y);
+            if (xi != cur) {
+                cur = xi;
+                if (xi >= 0) {
+                    cn.add(ST_XFORM_APPS);
+                    const DevXform x = sc.xforms[xi];
+                    ox = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; oy = r.oy + x.ty; oz = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
+                    dx = fmaf(x.c, r.dx, -x.s * r.dz); dy = r.dy; dz = fmaf(x.s, r.dx, x.c * r.dz);
+                } else {
+                    ox = r.ox; oy = r.oy; oz = r.oz; dx = r.dx; dy = r.dy; dz = r.dz;
+                }
+            }
+            float t;
+            if (rect_test_os(__float_as_uint(p.b.w) & 0xFFu, ox, oy, oz, dx, dy, dz, p, t_min, best.t, t)) {
+                cn.add(ST_RECT_ACCEPTS);
+                flat_consider(best, t, rid[i]);
+            }
+        }
+    }
+    return Hit{best.t, best.id};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,63 +348,57 @@ __device__ __forceinline__ bool slab(const BvhNode &n, const Ray &r, float idx, 
     return tn <= tf * 1.0000004f;
 }
 
-constexpr int kBvhStack = 48;
+constexpr int kBvhStack = 64;
+
+// stack entry / node reference: index in the low 28 bits, leaf primitive count in the top 4
+__device__ __forceinline__ uint32_t node_ref(uint32_t a, uint32_t b) { return a | (b << 28); }
 
 template <bool STATS>
 __device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
     const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-    const float inv_a = 1.0f / add;
-    const float idx = 1.0f / r.dx, idy = 1.0f / r.dy, idz = 1.0f / r.dz;
+    const float inv_a = rcp_approx(add);
+    const float idx = rcp_approx(r.dx), idy = rcp_approx(r.dy), idz = rcp_approx(r.dz);
     Hit h{__int_as_float(0x7f800000), kMiss};
+    if (sc.n_prims == 0) return h;
     uint32_t best_id = 0;
     uint32_t stack[kBvhStack];
     int sp = 0;
     const BvhNode *__restrict__ nodes = sc.nodes;
-    auto leaf = [&](uint32_t first, uint32_t count) {
-        for (uint32_t i = 0; i < count; ++i) {
-            const uint32_t slot = first + i;
-            const DevPrim p = sc.prims_bvh[slot];
-            float t;
-            if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
-                if (t < h.t || h.slot == kMiss) {
-                    h.t = t; h.slot = slot; best_id = sc.bvh_prim_id[slot];
-                } else {  // t == h.t
-                    const uint32_t id = sc.bvh_prim_id[slot];
-                    if (id > best_id) { h.slot = slot; best_id = id; }
+    uint32_t cur = node_ref(nodes[0].a, nodes[0].b);
+    for (;;) {
+        const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
+        if (cnt) {  // leaf: the only primitive-test site
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t slot = at + i;
+                const float4 *pp = reinterpret_cast<const float4 *>(sc.prims_bvh + slot);
+                DevPrim p;
+                p.a = __ldg(pp); p.b = __ldg(pp + 1);
+                float t;
+                if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
+                    const uint32_t id = __ldg(sc.bvh_prim_id + slot);
+                    if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
                 }
             }
+        } else {  // interior: fetch both children (one aligned 64-byte pair), ordered descent
+            const float4 *q = reinterpret_cast<const float4 *>(nodes + at);
+            const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+            const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
+            const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
+            cn.add(ST_NODE_TESTS, 2);
+            float tl, tr;
+            const bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
+            const bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
+            const uint32_t el = node_ref(L.a, L.b), er = node_ref(R.a, R.b);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                stack[sp++] = left_first ? er : el;  // depth is bounded by the builder (<= kBvhStack)
+                cur = left_first ? el : er;
+                continue;
+            }
+            if (hl || hr) { cur = hl ? el : er; continue; }
         }
-    };
-    if (sc.root_is_leaf) {
-        const BvhNode n = nodes[0];
-        leaf(n.a, n.b);
-        return h;
-    }
-    uint32_t cur = nodes[0].a;  // index of the root's left child; right = cur+1
-    for (;;) {
-        const float4 *q = reinterpret_cast<const float4 *>(nodes + cur);
-        const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
-        const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
-        const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
-        cn.add(ST_NODE_TESTS, 2);
-        float tl, tr;
-        bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
-        bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
-        // leaves are tested immediately; interiors are queued
-        if (hl && L.b) { leaf(L.a, L.b); hl = false; hr = hr && tr <= h.t; }
-        if (hr && R.b) { leaf(R.a, R.b); hr = false; hl = hl && tl <= h.t; }
-        if (hl && hr) {
-            const bool left_first = tl <= tr;
-            if (sp < kBvhStack) stack[sp++] = left_first ? R.a : L.a;
-            cur = left_first ? L.a : R.a;
-        } else if (hl) {
-            cur = L.a;
-        } else if (hr) {
-            cur = R.a;
-        } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
+        if (sp == 0) break;
+        cur = stack[--sp];
     }
     return h;
 }
