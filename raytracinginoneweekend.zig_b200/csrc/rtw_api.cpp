@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -259,8 +260,9 @@ int pick_variant(rtw_ctx *ctx, uint32_t requested, int *out, bool uses_smem = tr
         case RTW_VARIANT_WAVEFRONT: return fail(ctx, 1, "variant WAVEFRONT is not built yet");
         default: return fail(ctx, 1, "unknown variant %u", requested);
     }
-    if (v == VAR_FLAT && uses_smem && ctx->n_prims > kFlatHardMax)
-        return fail(ctx, 1, "flat variant holds at most %u primitives in shared memory (scene has %u)", kFlatHardMax, ctx->n_prims);
+    if (v == VAR_FLAT && uses_smem && (ctx->n_prims > kFlatHardMax || (size_t)ctx->scene.flat.total_f4 * 16 > 200 * 1024))
+        return fail(ctx, 1, "flat variant: the scene (%u primitives, %u B image) does not fit in shared memory", ctx->n_prims,
+                    ctx->scene.flat.total_f4 * 16u);
     *out = v;
     return 0;
 }
@@ -425,46 +427,118 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     std::vector<DevPrim> leaf_order(n);
     for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
 
-    // ---- shared-memory image for the flat scan: segmented by kind (FlatLayout) ------------------------
+    // ---- shared-memory image for the flat scan: segmented by kind, small spheres in groups of four --------
     FlatLayout fl{};
     std::vector<float4> blob;
     {
-        std::vector<float4> sph, big, mov, rect;
-        std::vector<uint32_t> id_sph, id_big, id_mov, id_rect;
+        std::vector<uint32_t> stat_ids, mov_ids, big_ids, rect_ids;
         for (uint32_t i = 0; i < n; ++i) {
             const rtw_prim &p = s->prims[i];
-            const DevPrim &d = flat[i];
             if (p.kind == RTW_PRIM_SPHERE) {
-                const float4 rec = make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w);
                 uint32_t meta;
-                std::memcpy(&meta, &d.b.w, 4);
-                if (meta >> 8) { big.push_back(rec); id_big.push_back(i); }  // same order as `bigs`
-                else { sph.push_back(rec); id_sph.push_back(i); }
-            } else if (p.kind == RTW_PRIM_MOVING_SPHERE) {
-                mov.push_back(make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w));
-                mov.push_back(make_float4(d.b.x, d.b.y, d.b.z, d.a.w));
-                id_mov.push_back(i);
-            } else {
-                rect.push_back(d.a); rect.push_back(d.b);
-                id_rect.push_back(i);
+                std::memcpy(&meta, &flat[i].b.w, 4);
+                ((meta >> 8) ? big_ids : stat_ids).push_back(i);  // big_ids in the same order as `bigs`
+            } else if (p.kind == RTW_PRIM_MOVING_SPHERE) mov_ids.push_back(i);
+            else rect_ids.push_back(i);
+        }
+        // spatial groups of exactly 4 (the last one may be short): recursive median splits on the widest
+        // axis of the centroids, the left half always a multiple of four so no slot is wasted
+        auto make_groups = [&](const std::vector<uint32_t> &sub) {
+            std::vector<std::vector<uint32_t>> groups;
+            std::vector<uint32_t> work(sub);
+            struct Range { size_t lo, hi; };
+            std::vector<Range> st;
+            if (!work.empty()) st.push_back({0, work.size()});
+            while (!st.empty()) {
+                const Range rg = st.back();
+                st.pop_back();
+                const size_t cnt = rg.hi - rg.lo;
+                if (cnt <= 4) {
+                    std::vector<uint32_t> m(work.begin() + rg.lo, work.begin() + rg.hi);
+                    std::sort(m.begin(), m.end());
+                    groups.push_back(m);
+                    continue;
+                }
+                double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+                auto cen = [&](uint32_t i, int a) { return 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]); };
+                for (size_t k = rg.lo; k < rg.hi; ++k)
+                    for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], cen(work[k], a)); mx[a] = std::max(mx[a], cen(work[k], a)); }
+                int ax = 0;
+                for (int a = 1; a < 3; ++a) if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
+                const size_t left = 4 * ((cnt / 4 + 1) / 2);  // multiple of 4, about half
+                std::nth_element(work.begin() + rg.lo, work.begin() + rg.lo + left, work.begin() + rg.hi,
+                                 [&](uint32_t x, uint32_t y) { return cen(x, ax) < cen(y, ax); });
+                st.push_back({rg.lo, rg.lo + left});
+                st.push_back({rg.lo + left, rg.hi});
+            }
+            return groups;
+        };
+        // sphere centre of prim i at time t (f64)
+        auto centre_at = [&](uint32_t i, double t, double c[3]) {
+            const rtw_prim &p = s->prims[i];
+            if (p.kind == RTW_PRIM_SPHERE) { c[0] = p.v[0]; c[1] = p.v[1]; c[2] = p.v[2]; return p.v[3]; }
+            const double u = (t - p.v[6]) / (p.v[7] - p.v[6]);
+            for (int a = 0; a < 3; ++a) c[a] = p.v[a] + (p.v[3 + a] - p.v[a]) * u;
+            return p.v[8];
+        };
+        auto bound_of = [&](const std::vector<uint32_t> &m) {
+            double cen[3] = {0, 0, 0};
+            for (uint32_t i : m)
+                for (int a = 0; a < 3; ++a) cen[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]) / (double)m.size();
+            double R = 0;
+            for (uint32_t i : m)
+                for (double t : {s->time0, s->time1}) {
+                    double c[3];
+                    const double r = centre_at(i, t, c);
+                    const double d = std::sqrt((c[0] - cen[0]) * (c[0] - cen[0]) + (c[1] - cen[1]) * (c[1] - cen[1]) + (c[2] - cen[2]) * (c[2] - cen[2]));
+                    R = std::max(R, d + r);
+                }
+            R = R * (1.0 + 1e-5) + 1e-6;  // fp32 evaluation slack
+            const float cf[3] = {(float)cen[0], (float)cen[1], (float)cen[2]};
+            for (int a = 0; a < 3; ++a) R += std::fabs((double)cf[a] - cen[a]);
+            return make_float4(cf[0], cf[1], cf[2], (float)(R * R * (1.0 + 1e-6)));
+        };
+        const auto sgroups = make_groups(stat_ids), mgroups = make_groups(mov_ids);
+        std::vector<float4> sph, big, mov, rect;
+        std::vector<uint32_t> ids;
+        const float4 dummy = make_float4(0.f, 0.f, 0.f, -1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (const auto &g : sgroups) {
+            sph.push_back(bound_of(g));
+            for (int k = 0; k < 4; ++k) {
+                if (k < (int)g.size()) {
+                    const DevPrim &d = flat[g[k]];
+                    sph.push_back(make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w));
+                    ids.push_back(g[k]);
+                } else { sph.push_back(dummy); ids.push_back(0); }
             }
         }
-        fl.n_sphere_real = (uint32_t)(id_sph.size() + id_big.size() + id_mov.size());
-        if (id_sph.size() & 1) { sph.push_back(make_float4(0.f, 0.f, 0.f, -1.f)); id_sph.push_back(0); }
-        if (id_mov.size() & 1) { mov.push_back(make_float4(0.f, 0.f, 0.f, -1.f)); mov.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); id_mov.push_back(0); }
-        fl.n_sph = (uint32_t)id_sph.size(); fl.n_big = (uint32_t)id_big.size();
-        fl.n_mov = (uint32_t)id_mov.size(); fl.n_rect = (uint32_t)id_rect.size();
+        for (uint32_t i : big_ids) {
+            const DevPrim &d = flat[i];
+            big.push_back(make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w));
+            ids.push_back(i);
+        }
+        while (ids.size() & 3) ids.push_back(0);
+        for (const auto &g : mgroups) {
+            mov.push_back(bound_of(g));
+            for (int k = 0; k < 4; ++k) {
+                if (k < (int)g.size()) {
+                    const DevPrim &d = flat[g[k]];
+                    mov.push_back(make_float4(d.a.x, d.a.y, d.a.z, d.a.w * d.a.w));
+                    mov.push_back(make_float4(d.b.x, d.b.y, d.b.z, d.a.w));
+                    ids.push_back(g[k]);
+                } else { mov.push_back(dummy); mov.push_back(zero4); ids.push_back(0); }
+            }
+        }
+        for (uint32_t i : rect_ids) { rect.push_back(flat[i].a); rect.push_back(flat[i].b); ids.push_back(i); }
+        while (ids.size() & 3) ids.push_back(0);
+        fl.n_sphere_real = (uint32_t)(stat_ids.size() + big_ids.size() + mov_ids.size());
+        fl.n_sph_groups = (uint32_t)sgroups.size(); fl.n_big = (uint32_t)big_ids.size();
+        fl.n_mov_groups = (uint32_t)mgroups.size(); fl.n_rect = (uint32_t)rect_ids.size();
         fl.off_sph = 0;
         fl.off_big = fl.off_sph + (uint32_t)sph.size();
         fl.off_mov = fl.off_big + (uint32_t)big.size();
         fl.off_rect = fl.off_mov + (uint32_t)mov.size();
         fl.off_ids = fl.off_rect + (uint32_t)rect.size();
-        std::vector<uint32_t> ids;
-        ids.insert(ids.end(), id_sph.begin(), id_sph.end());
-        ids.insert(ids.end(), id_big.begin(), id_big.end());
-        ids.insert(ids.end(), id_mov.begin(), id_mov.end());
-        ids.insert(ids.end(), id_rect.begin(), id_rect.end());
-        while (ids.size() & 3) ids.push_back(0);
         blob.insert(blob.end(), sph.begin(), sph.end());
         blob.insert(blob.end(), big.begin(), big.end());
         blob.insert(blob.end(), mov.begin(), mov.end());

@@ -73,15 +73,16 @@ struct DevPerlin {
 };
 
 // Shared-memory image of a small scene for the flat scan, as one blob of float4 (offsets in float4
-// units).  Primitives are SEGMENTED BY KIND so each scan loop is branch-free and unrollable:
-//   sph : static spheres        1 x float4 (cx, cy, cz, r^2)            count padded to even
-//   big : big static spheres    1 x float4 (cx, cy, cz, r^2), DevBigSphere i in scene.bigs
-//   mov : moving spheres        2 x float4 (cbx, cby, cbz, r^2), (vx, vy, vz, r)   padded to even
-//   rect: rects                 2 x float4 as DevPrim
-//   ids : uint32 prim id per entry, in the order sph | big | mov | rect
-// Padding entries have r^2 = -1 (never hit).
+// units).  Primitives are SEGMENTED BY KIND and small spheres are packed into spatial GROUPS of four
+// behind a bounding sphere, so that a whole warp can skip a group with one vote:
+//   sph groups : 5 x float4  = bound (cx, cy, cz, R^2) + 4 members (cx, cy, cz, r^2)
+//   big        : 1 x float4  (cx, cy, cz, r^2) per big static sphere; DevBigSphere i in scene.bigs
+//   mov groups : 9 x float4  = bound + 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}
+//   rect       : 2 x float4 as DevPrim
+//   ids        : uint32 prim id per member slot, in the order sph | big | mov | rect
+// Unused member slots have r^2 = -1 (never hit).
 struct FlatLayout {
-    uint32_t n_sph, n_big, n_mov, n_rect;  // loop trip counts (padded)
+    uint32_t n_sph_groups, n_big, n_mov_groups, n_rect;
     uint32_t off_sph, off_big, off_mov, off_rect, off_ids;
     uint32_t total_f4;
     uint32_t n_sphere_real;  // for the event counters

@@ -29,15 +29,17 @@ __device__ __forceinline__ void stage_flat(const DevScene &sc, float4 *s_flat) {
 }
 
 // One ray of one path: closest hit, then miss / shade.  Returns false when the path ended (its
-// radiance is then complete in L).
+// radiance is then complete in L).  Called by ALL lanes of the warp (the flat scan votes);
+// lanes without a path pass active = false and get false back.
 template <int VARIANT, bool STATS>
-__device__ __forceinline__ bool path_step(const DevScene &sc, const DevRender &rp, const float4 *s_flat, Ray &r,
-                                          uint32_t pixel, uint32_t sample, uint32_t &bounce, float3 &beta, float3 &L,
-                                          Counters<STATS> &cn) {
+__device__ __forceinline__ bool path_step(const DevScene &sc, const DevRender &rp, const float4 *s_flat, bool active,
+                                          Ray &r, uint32_t pixel, uint32_t sample, uint32_t &bounce, float3 &beta,
+                                          float3 &L, Counters<STATS> &cn) {
+    Hit h{0.0f, kMiss};
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<STATS>(r, active, s_flat, sc.flat, sc, 0.001f, cn);
+    else if (active) h = closest_hit_bvh<STATS>(r, sc, 0.001f, cn);
+    if (!active) return false;
     cn.add(ST_RAYS);
-    Hit h;
-    if (VARIANT == VAR_FLAT) h = closest_hit_flat<STATS>(r, s_flat, sc.flat, sc, 0.001f, cn);
-    else h = closest_hit_bvh<STATS>(r, sc, 0.001f, cn);
     if (h.slot == kMiss) {  // main.zig:109-112
         L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
         return false;
@@ -93,10 +95,9 @@ __global__ void __launch_bounds__(kBlock) k_megakernel(const DevScene sc, const 
                 cn.add(ST_PATHS);
             }
             if (!__any_sync(0xffffffffu, alive)) break;
-            if (alive) {
-                alive = path_step<VARIANT, STATS>(sc, rp, s_flat, r, pixel, cur_sample, bounce, beta, L, cn);
-                if (!alive) { sum.x += L.x; sum.y += L.y; sum.z += L.z; }
-            }
+            const bool was = alive;
+            alive = path_step<VARIANT, STATS>(sc, rp, s_flat, was, r, pixel, cur_sample, bounce, beta, L, cn);
+            if (was && !alive) { sum.x += L.x; sum.y += L.y; sum.z += L.z; }
         }
         if (inside) {
             float4 *dst = rp.accum + pixel;
@@ -182,10 +183,9 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_pooled(const DevScene sc,
             if (!more && pool_next == pool_end) break;
             continue;
         }
-        if (alive) {
-            alive = path_step<VARIANT, STATS>(sc, rp, s_flat, r, pixel, cur_sample, bounce, beta, L, cn);
-            if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
-        }
+        const bool was = alive;
+        alive = path_step<VARIANT, STATS>(sc, rp, s_flat, was, r, pixel, cur_sample, bounce, beta, L, cn);
+        if (was && !alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
     }
     if (STATS) cn.flush(rp.stats);
 }
@@ -235,13 +235,17 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
     if (VARIANT == VAR_FLAT) stage_flat(sc, s_flat);
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const float *q = rays + 7 * (size_t)idx;
-    Ray r{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+    const bool active = idx < n;
+    Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+    if (active) {
+        const float *q = rays + 7 * (size_t)idx;
+        r = Ray{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+    }
     Counters<false> cn;
-    Hit h;
-    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, s_flat, sc.flat, sc, 0.001f, cn);
-    else h = closest_hit_bvh<false>(r, sc, 0.001f, cn);
+    Hit h{0.0f, kMiss};
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, active, s_flat, sc.flat, sc, 0.001f, cn);
+    else if (active) h = closest_hit_bvh<false>(r, sc, 0.001f, cn);
+    if (!active) return;
     if (h.slot == kMiss) {
         prim_id[idx] = kMiss; t_out[idx] = 0.0f;
         normal[3 * idx] = normal[3 * idx + 1] = normal[3 * idx + 2] = 0.0f;

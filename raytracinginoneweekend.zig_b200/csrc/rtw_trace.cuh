@@ -177,12 +177,15 @@ __device__ __forceinline__ bool prim_test(const Ray &r, float add, float inv_a, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Flat scan: the scene staged in shared memory as a FlatLayout blob (segmented by primitive kind).
-// Every lane reads the same record (smem broadcast): the scan has no divergence, each loop body is
-// branch-free up to the (rare) accept path, and is unrolled by two for ILP.  Segmentation changes the
-// visiting order, so the reference's tie rule ("later list element wins", hittable.zig:235-242) is
-// applied explicitly: a candidate replaces the current hit if t < best, or t == best and its prim
-// id is larger.
+// Flat scan: the scene staged in shared memory as a FlatLayout blob.  Every lane reads the same
+// record (smem broadcast), so the scan itself has no divergence; loop bodies are branch-free up to
+// the (rare) accept path and unrolled for ILP.  Small spheres sit in spatial groups of four behind
+// a bounding sphere: each lane tests the bound, ONE warp vote decides whether anybody needs the
+// group, and if nobody does the whole warp skips its four members — culling without divergence.
+// ALL 32 lanes must call this (inactive lanes pass active = false): it contains warp votes.
+// Grouping changes the visiting order, so the reference's tie rule ("later list element wins",
+// hittable.zig:235-242) is applied explicitly: a candidate replaces the current hit if t < best, or
+// t == best and its prim id is larger.
 // ---------------------------------------------------------------------------------------------
 struct FlatBest {
     float t;
@@ -219,37 +222,54 @@ __device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, flo
     return true;
 }
 
+// does the ray (t >= 0) possibly touch the bounding sphere?  line test + "entirely behind" test
+__device__ __forceinline__ bool bound_hit(const Ray &r, float inv_a, const float4 b) {
+    float ox, oy, oz, bp;
+    const float d = sphere_disc(r, inv_a, b.x, b.y, b.z, b.w, ox, oy, oz, bp);
+    const float oo = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+    return d >= 0.0f && !(bp > 0.0f && oo > b.w);
+}
+
 template <bool STATS>
-__device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const float4 *s, const FlatLayout &L, const DevScene &sc,
-                                                float t_min, Counters<STATS> &cn) {
+__device__ __forceinline__ void flat_static_pair(const Ray &r, float add, float inv_a, const float4 a0, const float4 a1,
+                                                 uint32_t id0, uint32_t id1, bool active, float t_min, FlatBest &best,
+                                                 Counters<STATS> &cn) {
+    float o0x, o0y, o0z, b0, o1x, o1y, o1z, b1;
+    const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, o0x, o0y, o0z, b0);
+    const float d1 = sphere_disc(r, inv_a, a1.x, a1.y, a1.z, a1.w, o1x, o1y, o1z, b1);
+    if (active && d0 >= 0.0f) {
+        cn.add(ST_SPHERE_ROOTS);
+        const float c = fmaf(o0x, o0x, fmaf(o0y, o0y, fmaf(o0z, o0z, -a0.w)));
+        float t;
+        if (sphere_root(add, inv_a, c, b0, d0, t_min, best.t, t)) flat_consider(best, t, id0);
+    }
+    if (active && d1 >= 0.0f) {
+        cn.add(ST_SPHERE_ROOTS);
+        const float c = fmaf(o1x, o1x, fmaf(o1y, o1y, fmaf(o1z, o1z, -a1.w)));
+        float t;
+        if (sphere_root(add, inv_a, c, b1, d1, t_min, best.t, t)) flat_consider(best, t, id1);
+    }
+}
+
+template <bool STATS>
+__device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const float4 *s, const FlatLayout &L,
+                                                const DevScene &sc, float t_min, Counters<STATS> &cn) {
     const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
     const float inv_a = rcp_approx(add);
     FlatBest best{__int_as_float(0x7f800000), kMiss};
     const uint32_t *ids = reinterpret_cast<const uint32_t *>(s + L.off_ids);
-    cn.add(ST_SPHERE_TESTS, L.n_sphere_real);
 
-    // ---- static spheres: one LDS.128 per test ----
+    // ---- static sphere groups ----
     {
-        const float4 *sp = s + L.off_sph, *const se = sp + L.n_sph;
+        const float4 *gp = s + L.off_sph, *const ge = gp + 5 * L.n_sph_groups;
         const uint32_t *ip = ids;
 #pragma unroll 1
-        for (; sp < se; sp += 2, ip += 2) {
-            const float4 a0 = sp[0], a1 = sp[1];
-            float o0x, o0y, o0z, b0, o1x, o1y, o1z, b1;
-            const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, o0x, o0y, o0z, b0);
-            const float d1 = sphere_disc(r, inv_a, a1.x, a1.y, a1.z, a1.w, o1x, o1y, o1z, b1);
-            if (d0 >= 0.0f) {
-                cn.add(ST_SPHERE_ROOTS);
-                const float c = fmaf(o0x, o0x, fmaf(o0y, o0y, fmaf(o0z, o0z, -a0.w)));
-                float t;
-                if (sphere_root(add, inv_a, c, b0, d0, t_min, best.t, t)) flat_consider(best, t, ip[0]);
-            }
-            if (d1 >= 0.0f) {
-                cn.add(ST_SPHERE_ROOTS);
-                const float c = fmaf(o1x, o1x, fmaf(o1y, o1y, fmaf(o1z, o1z, -a1.w)));
-                float t;
-                if (sphere_root(add, inv_a, c, b1, d1, t_min, best.t, t)) flat_consider(best, t, ip[1]);
-            }
+        for (; gp < ge; gp += 5, ip += 4) {
+            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
+            if (active) cn.add(ST_SPHERE_TESTS, 4);
+            const uint4 id = *reinterpret_cast<const uint4 *>(ip);
+            flat_static_pair<STATS>(r, add, inv_a, gp[1], gp[2], id.x, id.y, active, t_min, best, cn);
+            flat_static_pair<STATS>(r, add, inv_a, gp[3], gp[4], id.z, id.w, active, t_min, best, cn);
         }
     }
     // ---- big static spheres: c term about the reference point ----
@@ -259,7 +279,8 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const float4 *s, c
             const float4 a0 = sp[i];
             float ox, oy, oz, bp;
             const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, ox, oy, oz, bp);
-            if (d0 >= 0.0f) {
+            if (active) cn.add(ST_SPHERE_TESTS);
+            if (active && d0 >= 0.0f) {
                 cn.add(ST_SPHERE_ROOTS);
                 const DevBigSphere g = sc.bigs[i];
                 const float ax = r.ox - g.qx, ay = r.oy - g.qy, az = r.oz - g.qz;
@@ -267,51 +288,43 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const float4 *s, c
                 const float am = fmaf(ax, g.mx, fmaf(ay, g.my, az * g.mz));
                 const float c = fmaf(2.0f, am, aa) + g.K;
                 float t;
-                if (sphere_root(add, inv_a, c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[L.n_sph + i]);
+                if (sphere_root(add, inv_a, c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[4 * L.n_sph_groups + i]);
             }
         }
     }
-    // ---- moving spheres: centre(time) = cb + vel*time (hittable.zig:219-221) ----
+    // ---- moving sphere groups: centre(time) = cb + vel*time (hittable.zig:219-221) ----
     {
-        const float4 *sp = s + L.off_mov, *const se = sp + 2 * L.n_mov;
-        const uint32_t *ip = ids + L.n_sph + L.n_big;
+        const float4 *gp = s + L.off_mov, *const ge = gp + 9 * L.n_mov_groups;
+        const uint32_t *ip = ids + 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u);
 #pragma unroll 1
-        for (; sp < se; sp += 4, ip += 2) {
-            const float4 a0 = sp[0], v0 = sp[1], a1 = sp[2], v1 = sp[3];
-            float o0x, o0y, o0z, b0, o1x, o1y, o1z, b1;
-            const float d0 = sphere_disc(r, inv_a, fmaf(v0.x, r.time, a0.x), fmaf(v0.y, r.time, a0.y),
-                                         fmaf(v0.z, r.time, a0.z), a0.w, o0x, o0y, o0z, b0);
-            const float d1 = sphere_disc(r, inv_a, fmaf(v1.x, r.time, a1.x), fmaf(v1.y, r.time, a1.y),
-                                         fmaf(v1.z, r.time, a1.z), a1.w, o1x, o1y, o1z, b1);
-            if (d0 >= 0.0f) {
-                cn.add(ST_SPHERE_ROOTS);
-                const float c = fmaf(o0x, o0x, fmaf(o0y, o0y, fmaf(o0z, o0z, -a0.w)));
-                float t;
-                if (sphere_root(add, inv_a, c, b0, d0, t_min, best.t, t)) flat_consider(best, t, ip[0]);
-            }
-            if (d1 >= 0.0f) {
-                cn.add(ST_SPHERE_ROOTS);
-                const float c = fmaf(o1x, o1x, fmaf(o1y, o1y, fmaf(o1z, o1z, -a1.w)));
-                float t;
-                if (sphere_root(add, inv_a, c, b1, d1, t_min, best.t, t)) flat_consider(best, t, ip[1]);
+        for (; gp < ge; gp += 9, ip += 4) {
+            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
+            if (active) cn.add(ST_SPHERE_TESTS, 4);
+            const uint4 id = *reinterpret_cast<const uint4 *>(ip);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 a0 = gp[1 + 4 * h], v0 = gp[2 + 4 * h], a1 = gp[3 + 4 * h], v1 = gp[4 + 4 * h];
+                const float4 c0 = make_float4(fmaf(v0.x, r.time, a0.x), fmaf(v0.y, r.time, a0.y), fmaf(v0.z, r.time, a0.z), a0.w);
+                const float4 c1 = make_float4(fmaf(v1.x, r.time, a1.x), fmaf(v1.y, r.time, a1.y), fmaf(v1.z, r.time, a1.z), a1.w);
+                flat_static_pair<STATS>(r, add, inv_a, c0, c1, h ? id.z : id.x, h ? id.w : id.y, active, t_min, best, cn);
             }
         }
     }
     // ---- rects: the instance transform is recomputed only when the (warp-uniform) xform id changes ----
     {
         const float4 *rp = s + L.off_rect;
-        const uint32_t *rid = ids + L.n_sph + L.n_big + L.n_mov;
+        const uint32_t *rid = ids + 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u) + 4 * L.n_mov_groups;
         int cur = -1;
         float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
         for (uint32_t i = 0; i < L.n_rect; ++i) {
             DevPrim p;
             p.a = rp[2 * i]; p.b = rp[2 * i + 1];
-            cn.add(ST_RECT_TESTS);
+            if (active) cn.add(ST_RECT_TESTS);
             const int xi = __float_as_int(p.b.y);
             if (xi != cur) {
                 cur = xi;
                 if (xi >= 0) {
-                    cn.add(ST_XFORM_APPS);
+                    if (active) cn.add(ST_XFORM_APPS);
                     const DevXform x = sc.xforms[xi];
                     ox = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; oy = r.oy + x.ty; oz = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
                     dx = fmaf(x.c, r.dx, -x.s * r.dz); dy = r.dy; dz = fmaf(x.s, r.dx, x.c * r.dz);
@@ -320,7 +333,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, const float4 *s, c
                 }
             }
             float t;
-            if (rect_test_os(__float_as_uint(p.b.w) & 0xFFu, ox, oy, oz, dx, dy, dz, p, t_min, best.t, t)) {
+            if (active && rect_test_os(__float_as_uint(p.b.w) & 0xFFu, ox, oy, oz, dx, dy, dz, p, t_min, best.t, t)) {
                 cn.add(ST_RECT_ACCEPTS);
                 flat_consider(best, t, rid[i]);
             }
