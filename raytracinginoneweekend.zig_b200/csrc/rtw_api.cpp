@@ -645,6 +645,7 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     rp.max_depth = p->max_depth;
     rp.seed_lo = (uint32_t)p->seed; rp.seed_hi = (uint32_t)(p->seed >> 32);
     rp.bg_r = (float)p->background[0]; rp.bg_g = (float)p->background[1]; rp.bg_b = (float)p->background[2];
+    rp.inv_wm1 = (float)(1.0 / ((double)p->width - 1.0)); rp.inv_hm1 = (float)(1.0 / ((double)p->height - 1.0));
     rp.accum = reinterpret_cast<float4 *>(d_accum);
     rp.tile_counter = ctx->tile_counter.p;
     rp.stats = ctx->stat_counters.p;
@@ -673,6 +674,9 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     rp.n_sblocks = (spp + kBatchSpp - 1) / kBatchSpp;
     if ((uint64_t)rp.n_sblocks * rp.n_tiles > 0xFFFFFFF0ull) return fail(ctx, 1, "too many path batches for one launch");
     rp.n_batches = rp.n_sblocks * rp.n_tiles;
+    rp.service_threshold = 12; rp.steps_per_round = 2;
+    if (const char *e = getenv("RTW_BVH_THRESH")) rp.service_threshold = (uint32_t)std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("RTW_BVH_STEPS")) rp.steps_per_round = (uint32_t)std::max(1, std::min(64, atoi(e)));
 
     if (spp == 0) { ctx->stats.n_launches = 0; return 0; }
     if (stats) CK(cudaMemsetAsync(ctx->stat_counters.p, 0, ST_COUNT * sizeof(unsigned long long), st));

@@ -130,9 +130,11 @@ struct DevRender {
     uint32_t max_depth;
     uint32_t seed_lo, seed_hi;
     float bg_r, bg_g, bg_b;
+    float inv_wm1, inv_hm1;        // 1/(W-1), 1/(H-1)  (main.zig:390-391)
     float4 *accum;                 // width*height, row j = reference scanline j
     unsigned int *tile_counter;    // persistent-kernel work queue (tiles x chunks, or path batches)
     uint32_t n_batches, n_sblocks, batch_spp;  // pooled kernel: batch = one tile x batch_spp samples
+    uint32_t service_threshold, steps_per_round;  // BVH state machine tuning
     unsigned long long *stats;     // ST_COUNT counters (instrumented build only)
     uint32_t n_tiles, tiles_x, spp_chunk, n_chunks;
 };

@@ -191,6 +191,95 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_pooled(const DevScene sc,
 }
 
 // ---------------------------------------------------------------------------------------------
+// BVH megakernel (pooled): a per-lane state machine.  BVH traversals have very different lengths
+// (measured: 11.6 of 32 lanes active when every lane runs its traversal to completion before the warp
+// shades), so here the warp interleaves: lanes that are traversing take one traversal step per
+// iteration; lanes whose traversal is finished wait until at least rp.service_threshold of them have
+// gathered (or nobody is traversing), then they are shaded, dead paths are replaced from the pool and
+// new traversals start — all in one "service" phase that therefore runs reasonably full.
+// ---------------------------------------------------------------------------------------------
+
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, const DevCamera cam, const DevRender rp) {
+    Counters<STATS> cn;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t pool_next = 0, pool_end = 0, pool_tx = 0, pool_ty = 0, pool_s0 = 0;
+    bool more = true;
+
+    float3 beta = make_float3(1.0f, 1.0f, 1.0f), L = make_float3(0.0f, 0.0f, 0.0f);
+    Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+    uint32_t bounce = 0, cur_sample = 0, pixel = 0;
+    bool alive = false, trav = false;
+    BvhTraversal tv;
+    tv.sp = 0; tv.cur = 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xffffffffu, !trav);
+        if (__popc(idle) >= (int)rp.service_threshold) {
+            // ---- service phase: shade finished traversals ----
+            if (!trav && alive) {
+                cn.add(ST_RAYS);
+                if (tv.h.slot == kMiss) {  // main.zig:109-112
+                    L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
+                    alive = false;
+                } else {
+                    const DevPrim prim = sc.prims_bvh[tv.h.slot];
+                    const uint32_t prim_id = sc.bvh_prim_id[tv.h.slot];
+                    ++bounce;
+                    alive = shade<STATS>(sc, rp, r, prim, prim_id, tv.h.t, pixel, cur_sample, bounce, beta, L, cn) &&
+                            bounce < rp.max_depth;  // main.zig:105-108
+                }
+                if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
+            }
+            // ---- hand new paths to lanes without one ----
+            for (;;) {
+                const uint32_t need = __ballot_sync(0xffffffffu, !alive);
+                if (!need) break;
+                if (pool_next == pool_end) {
+                    if (!more) break;
+                    uint32_t b = 0;
+                    if (lane == 0) b = atomicAdd(rp.tile_counter, 1u);
+                    b = __shfl_sync(0xffffffffu, b, 0);
+                    if (b >= rp.n_batches) { more = false; break; }
+                    const uint32_t sb = b / rp.n_tiles, tile = b - sb * rp.n_tiles;
+                    pool_ty = tile / rp.tiles_x; pool_tx = tile - pool_ty * rp.tiles_x;
+                    pool_s0 = rp.spp_begin + sb * rp.batch_spp;
+                    pool_next = 0;
+                    pool_end = 32u * min(rp.batch_spp, rp.spp_end - pool_s0);
+                }
+                const uint32_t take = min((uint32_t)__popc(need), pool_end - pool_next);
+                const uint32_t rank = __popc(need & lt_mask);
+                if (!alive && rank < take) {
+                    const uint32_t idx = pool_next + rank;
+                    const uint32_t pl = idx & 31u;
+                    const uint32_t i = pool_tx * 8 + (pl & 7), j = pool_ty * 4 + (pl >> 3);
+                    if (i < rp.width && j < rp.height) {
+                        pixel = j * rp.width + i;
+                        cur_sample = pool_s0 + (idx >> 5);
+                        r = camera_ray(cam, rp, pixel, i, j, cur_sample);
+                        beta = make_float3(1.0f, 1.0f, 1.0f);
+                        L = make_float3(0.0f, 0.0f, 0.0f);
+                        bounce = 0;
+                        alive = true;
+                        cn.add(ST_PATHS);
+                    }
+                }
+                pool_next += take;
+            }
+            // ---- start the traversal of every lane that has a ray and is not traversing ----
+            if (alive && !trav) trav = !tv.init(r, sc);
+            if (!__any_sync(0xffffffffu, alive)) break;  // pool exhausted and every path finished
+        }
+        // ---- traversal phase ----
+#pragma unroll 1
+        for (uint32_t k = 0; k < rp.steps_per_round; ++k) {
+            if (trav) trav = !tv.template step<STATS>(r, sc, 0.001f, cn);
+        }
+    }
+    if (STATS) cn.flush(rp.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4 resolve: out = 256 * clamp(sqrt(sum / spp), 0, 0.999) truncated to u8, written to row H-1-j.
 // Sums up to kMaxResolveBufs accumulation buffers first; with peer access enabled those may live on
 // other GPUs, i.e. the cross-GPU reduction and the resolve are one kernel over NVLink peer memory.
@@ -290,9 +379,16 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // host-side launchers (called from rtw_api.cpp through rtw_kernels.h)
 // ---------------------------------------------------------------------------------------------
 template <int VARIANT, bool STATS, bool POOLED>
+static auto mega_kernel_ptr() {
+    if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS>;
+    else if constexpr (POOLED) return k_megakernel_pooled<VARIANT, STATS>;
+    else return k_megakernel<VARIANT, STATS>;
+}
+
+template <int VARIANT, bool STATS, bool POOLED>
 static cudaError_t launch_mega_t(const DevScene &sc, const DevCamera &cam, const DevRender &rp, int grid,
                                  size_t smem, cudaStream_t st) {
-    auto kern = POOLED ? k_megakernel_pooled<VARIANT, STATS> : k_megakernel<VARIANT, STATS>;
+    auto kern = mega_kernel_ptr<VARIANT, STATS, POOLED>();
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -317,7 +413,7 @@ cudaError_t launch_megakernel(int variant, bool stats, bool pooled, const DevSce
 
 template <int VARIANT, bool STATS, bool POOLED>
 static int occ_t(size_t smem) {
-    auto kern = POOLED ? k_megakernel_pooled<VARIANT, STATS> : k_megakernel<VARIANT, STATS>;
+    auto kern = mega_kernel_ptr<VARIANT, STATS, POOLED>();
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int n = 0;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, smem) == cudaSuccess ? n : 0;

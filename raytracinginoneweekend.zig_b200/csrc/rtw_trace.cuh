@@ -366,34 +366,36 @@ constexpr int kBvhStack = 64;
 // stack entry / node reference: index in the low 28 bits, leaf primitive count in the top 4
 __device__ __forceinline__ uint32_t node_ref(uint32_t a, uint32_t b) { return a | (b << 28); }
 
-template <bool STATS>
-__device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
-    const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-    const float inv_a = rcp_approx(add);
-    const float idx = rcp_approx(r.dx), idy = rcp_approx(r.dy), idz = rcp_approx(r.dz);
-    Hit h{__int_as_float(0x7f800000), kMiss};
-    if (sc.n_prims == 0) return h;
-    uint32_t best_id = 0;
+// Traversal state of one ray.  `step` performs at most one interior visit (both children of the
+// current node) followed by at most one leaf visit, so a warp can interleave traversal steps of its
+// lanes with shading/regeneration of the lanes that are done (k_megakernel_bvh).
+struct BvhTraversal {
+    float idx, idy, idz, add, inv_a;
+    Hit h;
+    uint32_t best_id;
+    uint32_t cur;  // node_ref of the node to visit next
+    int sp;
     uint32_t stack[kBvhStack];
-    int sp = 0;
-    const BvhNode *__restrict__ nodes = sc.nodes;
-    uint32_t cur = node_ref(nodes[0].a, nodes[0].b);
-    for (;;) {
-        const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
-        if (cnt) {  // leaf: the only primitive-test site
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const uint32_t slot = at + i;
-                const float4 *pp = reinterpret_cast<const float4 *>(sc.prims_bvh + slot);
-                DevPrim p;
-                p.a = __ldg(pp); p.b = __ldg(pp + 1);
-                float t;
-                if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
-                    const uint32_t id = __ldg(sc.bvh_prim_id + slot);
-                    if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
-                }
-            }
-        } else {  // interior: fetch both children (one aligned 64-byte pair), ordered descent
-            const float4 *q = reinterpret_cast<const float4 *>(nodes + at);
+
+    // returns true when the traversal is already finished (empty scene)
+    __device__ __forceinline__ bool init(const Ray &r, const DevScene &sc) {
+        add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
+        inv_a = rcp_approx(add);
+        idx = rcp_approx(r.dx); idy = rcp_approx(r.dy); idz = rcp_approx(r.dz);
+        h = Hit{__int_as_float(0x7f800000), kMiss};
+        best_id = 0;
+        sp = 0;
+        if (sc.n_prims == 0) return true;
+        const BvhNode root = sc.nodes[0];
+        cur = node_ref(root.a, root.b);
+        return false;
+    }
+
+    // returns true when the traversal is finished
+    template <bool STATS>
+    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+        if (!(cur >> 28)) {  // interior: fetch both children (one aligned 64-byte pair), ordered descent
+            const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
             const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
             const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
             const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
@@ -406,14 +408,39 @@ __device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc,
                 const bool left_first = tl <= tr;
                 stack[sp++] = left_first ? er : el;  // depth is bounded by the builder (<= kBvhStack)
                 cur = left_first ? el : er;
-                continue;
+            } else if (hl || hr) {
+                cur = hl ? el : er;
+            } else {
+                if (sp == 0) return true;
+                cur = stack[--sp];
             }
-            if (hl || hr) { cur = hl ? el : er; continue; }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        if (cur >> 28) {  // leaf: the only primitive-test site
+            const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t slot = at + i;
+                const float4 *pp = reinterpret_cast<const float4 *>(sc.prims_bvh + slot);
+                DevPrim p;
+                p.a = __ldg(pp); p.b = __ldg(pp + 1);
+                float t;
+                if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
+                    const uint32_t id = __ldg(sc.bvh_prim_id + slot);
+                    if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
+                }
+            }
+            if (sp == 0) return true;
+            cur = stack[--sp];
+        }
+        return false;
     }
-    return h;
+};
+
+template <bool STATS>
+__device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+    BvhTraversal tv;
+    if (tv.init(r, sc)) return tv.h;
+    while (!tv.template step<STATS>(r, sc, t_min, cn)) {}
+    return tv.h;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,7 +465,7 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
     if (kind == PK_SPHERE) {
         cn.add(ST_SPHERE_FINAL);
         const float cx = fmaf(p.b.x, r.time, p.a.x), cy = fmaf(p.b.y, r.time, p.a.y), cz = fmaf(p.b.z, r.time, p.a.z);
-        const float inv_r = 1.0f / p.a.w;
+        const float inv_r = rcp_approx(p.a.w);
         s.onx = (s.px - cx) * inv_r; s.ony = (s.py - cy) * inv_r; s.onz = (s.pz - cz) * inv_r;
         s.is_sphere = true;
         s.u = 0.0f; s.v = 0.0f;
@@ -459,8 +486,8 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
         if (kind == PK_XY) { pa = qx; pb = qy; nzo = 1.0f; }
         else if (kind == PK_XZ) { pa = qx; pb = qz; nyo = 1.0f; }
         else { pa = qy; pb = qz; nxo = 1.0f; }
-        s.u = (pa - p.a.x) / (p.a.y - p.a.x);
-        s.v = (pb - p.a.z) / (p.a.w - p.a.z);
+        s.u = __fdividef(pa - p.a.x, p.a.y - p.a.x);
+        s.v = __fdividef(pb - p.a.z, p.a.w - p.a.z);
         // object -> world for the normal (RotateY.hit hittable.zig:588-590): n = A^T n_obj
         s.onx = fmaf(x.c, nxo, x.s * nzo);
         s.ony = nyo;
@@ -550,7 +577,7 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, cons
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float3 sample_unit_vector(float u1, float u2) {  // randomUnitVector rand.zig:38-40
     const float z = 1.0f - 2.0f * u1;
-    const float rxy = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    const float rxy = sqrt_approx(fmaxf(0.0f, 1.0f - z * z));
     float sn, cs;
     __sincosf(6.28318530717958647692f * u2, &sn, &cs);
     return make_float3(rxy * cs, rxy * sn, z);
@@ -561,7 +588,7 @@ __device__ __forceinline__ float3 sample_unit_ball(float u1, float u2, float u3)
     return make_float3(d.x * rad, d.y * rad, d.z * rad);
 }
 __device__ __forceinline__ float2 sample_unit_disk(float u1, float u2) {  // randomPointInUnitDisk rand.zig:30-36
-    const float rad = sqrtf(u1);
+    const float rad = sqrt_approx(u1);
     float sn, cs;
     __sincosf(6.28318530717958647692f * u2, &sn, &cs);
     return make_float2(rad * cs, rad * sn);
@@ -575,8 +602,8 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera &cam, const DevRender 
     const float ju = u01_24(rn.x), jv = u01_24(rn.y);
     const float l1 = u01_24(rn.z), l2 = u01_24(rn.w);
     const float tm = u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8));
-    const float s = ((float)i + ju) / ((float)rp.width - 1.0f);
-    const float t = ((float)j + jv) / ((float)rp.height - 1.0f);
+    const float s = ((float)i + ju) * rp.inv_wm1;  // main.zig:390-391 (division by W-1 as a multiply)
+    const float t = ((float)j + jv) * rp.inv_hm1;
     const float2 dk = sample_unit_disk(l1, l2);
     const float rdx = dk.x * cam.lens_radius, rdy = dk.y * cam.lens_radius;
     const float offx = cam.ux * rdx + cam.wx * rdy, offy = cam.uy * rdx + cam.wy * rdy, offz = cam.uz * rdx + cam.wz * rdy;
@@ -633,18 +660,18 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, R
             if (!(fmaf(rx, s.nx, fmaf(ry, s.ny, rz * s.nz)) > 0.0f)) return false;
         } else {  // dielectric material.zig:72-85
             cn.add(ST_SC_DIELECTRIC);
-            const float ratio = s.front_face ? 1.0f / m.param : m.param;
+            const float ratio = s.front_face ? rcp_approx(m.param) : m.param;
             const float cos_theta = fminf(-udn, 1.0f);
-            const float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+            const float sin_theta = sqrt_approx(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
             const bool can_refract = ratio * sin_theta <= 1.0f;
-            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            float r0 = __fdividef(1.0f - ratio, 1.0f + ratio);
             r0 *= r0;
             const float om = 1.0f - cos_theta, om2 = om * om;
             const float refl = fmaf(1.0f - r0, om2 * om2 * om, r0);  // Schlick material.zig:87-91
             if (can_refract && refl < u01_24(rn.x)) {  // refract material.zig:116-121
                 const float px = ratio * fmaf(cos_theta, s.nx, ux), py = ratio * fmaf(cos_theta, s.ny, uy),
                             pz = ratio * fmaf(cos_theta, s.nz, uz);
-                const float par = -sqrtf(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
+                const float par = -sqrt_approx(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
                 ndx = fmaf(par, s.nx, px); ndy = fmaf(par, s.ny, py); ndz = fmaf(par, s.nz, pz);
             } else {  // reflect material.zig:112-114
                 ndx = fmaf(-2.0f * udn, s.nx, ux); ndy = fmaf(-2.0f * udn, s.ny, uy); ndz = fmaf(-2.0f * udn, s.nz, uz);
