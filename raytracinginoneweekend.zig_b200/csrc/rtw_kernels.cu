@@ -126,7 +126,7 @@ __device__ __forceinline__ void red_add_v4(float4 *addr, float x, float y, float
 }
 
 template <int VARIANT, bool STATS>
-__global__ void __launch_bounds__(kBlock) k_megakernel_pooled(const DevScene sc, const DevCamera cam, const DevRender rp) {
+__global__ void __launch_bounds__(kBlock, 9) k_megakernel_pooled(const DevScene sc, const DevCamera cam, const DevRender rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
     if (VARIANT == VAR_FLAT) stage_flat(sc, s_flat);

@@ -265,6 +265,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
         const uint32_t *ip = ids;
 #pragma unroll 1
         for (; gp < ge; gp += 5, ip += 4) {
+            if (active) cn.add(ST_SPHERE_TESTS);  // the bound is a sphere test too
             if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
             if (active) cn.add(ST_SPHERE_TESTS, 4);
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
@@ -298,6 +299,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
         const uint32_t *ip = ids + 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u);
 #pragma unroll 1
         for (; gp < ge; gp += 9, ip += 4) {
+            if (active) cn.add(ST_SPHERE_TESTS);
             if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
             if (active) cn.add(ST_SPHERE_TESTS, 4);
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
