@@ -301,7 +301,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
         for (; gp < ge; gp += 9, ip += 4) {
             if (active) cn.add(ST_SPHERE_TESTS);
             if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
-            if (active) cn.add(ST_SPHERE_TESTS, 4);
+            if (active) { cn.add(ST_SPHERE_TESTS, 4); cn.add(ST_MOVING_TESTS, 4); }
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
