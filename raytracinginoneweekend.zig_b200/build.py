@@ -53,6 +53,7 @@ def build_cuda(force=False, verbose=False, extra=()):
     hdrs = _deps(CSRC, (".h", ".cuh")) + [os.path.join(ROOT, "include", "rtw_cuda.h"), os.path.abspath(__file__)]
     units = [
         ("rtw_kernels.cu", ["-Xptxas", "-v"]),          # production arithmetic: FMA contraction on
+        ("rtw_wavefront.cu", []),                       # K2 wavefront schedule (same device functions)
         ("rtw_probe.cu", ["-fmad=false"]),              # reference-order probe: no contraction, IEEE div/sqrt
         ("rtw_api.cpp", []),
         ("rtw_bvh.cpp", []),

@@ -92,6 +92,13 @@ struct rtw_ctx {
     uint32_t n_prims = 0;
     bool root_is_leaf = false;
 
+    // wavefront variant: path-state slots
+    DevBuf<float4> wf_ro, wf_rd, wf_beta, wf_rad;
+    DevBuf<uint32_t> wf_hit, wf_free0, wf_free1, wf_cursor;
+    DevBuf<WfCounters> wf_counters;
+    WfCounters *wf_host_counters = nullptr;
+    uint32_t wf_slots = 0;
+
     DevBuf<float4> accum;       // internal accumulation buffer of rtw_cuda_render
     DevBuf<uint8_t> rgb8;
     DevBuf<unsigned int> tile_counter;
@@ -257,7 +264,7 @@ int pick_variant(rtw_ctx *ctx, uint32_t requested, int *out, bool uses_smem = tr
         case RTW_VARIANT_AUTO: v = ctx->n_prims <= kFlatAutoMax ? VAR_FLAT : VAR_BVH; break;
         case RTW_VARIANT_MEGA_FLAT: v = VAR_FLAT; break;
         case RTW_VARIANT_MEGA_BVH: v = VAR_BVH; break;
-        case RTW_VARIANT_WAVEFRONT: return fail(ctx, 1, "variant WAVEFRONT is not built yet");
+        case RTW_VARIANT_WAVEFRONT: v = ctx->n_prims <= kFlatAutoMax ? VAR_FLAT : VAR_BVH; break;  // traversal of the wavefront
         default: return fail(ctx, 1, "unknown variant %u", requested);
     }
     if (v == VAR_FLAT && uses_smem && (ctx->n_prims > kFlatHardMax || (size_t)ctx->scene.flat.total_f4 * 16 > 200 * 1024))
@@ -309,6 +316,9 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
     cudaDeviceSynchronize();
     free_images(ctx);
     ctx->flat_blob.release();
+    ctx->wf_ro.release(); ctx->wf_rd.release(); ctx->wf_beta.release(); ctx->wf_rad.release(); ctx->wf_hit.release();
+    ctx->wf_free0.release(); ctx->wf_free1.release(); ctx->wf_cursor.release(); ctx->wf_counters.release();
+    if (ctx->wf_host_counters) cudaFreeHost(ctx->wf_host_counters);
     ctx->prims_flat.release(); ctx->prims_bvh.release(); ctx->bvh_prim_id.release(); ctx->prim_material.release();
     ctx->nodes.release(); ctx->xforms.release(); ctx->bigs.release(); ctx->materials.release(); ctx->textures.release();
     ctx->images.release(); ctx->perlins.release(); ctx->raw_prims.release(); ctx->raw_chains.release();
@@ -683,6 +693,29 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     CK(cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned int), st));
     const DevCamera dc = lower_camera(cam);
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
+    if (p->variant == RTW_VARIANT_WAVEFRONT) {
+        // K2: host loop of generate / extend / shade launches over the path-state slots (blocks the caller)
+        uint32_t slots = 1u << 21;
+        if (const char *e = getenv("RTW_WF_SLOTS")) slots = (uint32_t)std::max(128l, atol(e));
+        slots = (slots + 127u) & ~127u;
+        if (ctx->wf_slots != slots) {
+            CK(ctx->wf_ro.alloc(slots)); CK(ctx->wf_rd.alloc(slots)); CK(ctx->wf_beta.alloc(slots)); CK(ctx->wf_rad.alloc(slots));
+            CK(ctx->wf_hit.alloc(slots)); CK(ctx->wf_free0.alloc(slots)); CK(ctx->wf_free1.alloc(slots));
+            CK(ctx->wf_cursor.alloc(1)); CK(ctx->wf_counters.alloc(1));
+            if (!ctx->wf_host_counters) CK(cudaMallocHost(&ctx->wf_host_counters, sizeof(WfCounters)));
+            ctx->wf_slots = slots;
+        }
+        WfState ws{};
+        ws.ro = ctx->wf_ro.p; ws.rd = ctx->wf_rd.p; ws.beta = ctx->wf_beta.p; ws.rad = ctx->wf_rad.p; ws.hit = ctx->wf_hit.p;
+        ws.free_list[0] = ctx->wf_free0.p; ws.free_list[1] = ctx->wf_free1.p;
+        ws.counters = ctx->wf_counters.p; ws.extend_cursor = ctx->wf_cursor.p; ws.n_slots = slots;
+        uint32_t nl = 0;
+        CK(wavefront_accumulate(ws, variant, stats, ctx->scene, dc, rp, ctx->n_sms, ctx->wf_host_counters, st, &nl));
+        if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+        ctx->stats.n_launches = nl;
+        ctx->stats.variant_used = RTW_VARIANT_WAVEFRONT;
+        return 0;
+    }
     CK(launch_megakernel(variant, stats, pooled, ctx->scene, dc, rp, grid, st));
     if (timed) CK(cudaEventRecord(ctx->ev[1], st));
     ctx->stats.n_launches = 1;

@@ -28,6 +28,25 @@ cudaError_t launch_probe(int variant, const DevScene &sc, uint32_t n, const floa
                          float *normal, float *uv, cudaStream_t st);
 cudaError_t launch_ffma_peak(float *out, int grid, int iters, cudaStream_t st);
 
+// rtw_wavefront.cu (K2: wavefront schedule of the same path)
+struct WfCounters {
+    uint32_t n_free[2];
+    uint32_t pad[2];
+    unsigned long long next_path[2];
+};
+struct WfState {
+    float4 *ro, *rd, *beta, *rad;  // (o.xyz, time) (d.xyz, t_hit) (beta.rgb, pixel) (L.rgb, sample<<6|bounce)
+    uint32_t *hit;
+    uint32_t *free_list[2];
+    WfCounters *counters;
+    uint32_t *extend_cursor;
+    uint32_t n_slots;
+    unsigned long long total_paths;
+};
+cudaError_t wavefront_accumulate(WfState &st, int variant, bool stats, const DevScene &sc, const DevCamera &cam,
+                                 const DevRender &rp, int n_sms, WfCounters *h_counters, cudaStream_t stream,
+                                 uint32_t *n_launches_out);
+
 // rtw_probe.cu (reference-order arithmetic, compiled with -fmad=false; parity instrument only).
 // The raw scene keeps the reference's f64 fields and its nested instance chains.
 struct RawXform {

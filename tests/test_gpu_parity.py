@@ -376,6 +376,30 @@ def test_white_furnace_on_device(rtw, ctx):
         assert acc[..., :3].max() == 0.0
 
 
+@pytest.mark.parametrize("sid,grid,W,H,spp", [(1, 3, 200, 120, 33), (6, 3, 97, 61, 40), (1, 11, 160, 90, 16), (7, 3, 120, 68, 24)])
+def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, monkeypatch, sid, grid, W, H, spp):
+    """K2 (generate / extend / shade+compact) is a different schedule of the same path: identical Philox keys and
+    identical closest hits => identical per-sample radiance; only fp32 summation order differs.  Ragged frame
+    sizes and a small slot count force many refill iterations."""
+    monkeypatch.setenv("RTW_WF_SLOTS", "8192")
+    hs = rtw.HostScene(sid, grid=grid)
+    ctx.upload_scene(hs.desc, keep=hs)
+    cam = hs.camera(aspect=W / H)
+    flag = rtw.abi.FLAG_COUNT_EVENTS
+    mega = ctx.render(cam, ctx.params(W, H, 0, spp, spp, 50, rtw.abi.VARIANT_AUTO, flag, 42, hs.background), want_accum=True)
+    st_m = ctx.stats()
+    wave = ctx.render(cam, ctx.params(W, H, 0, spp, spp, 50, rtw.abi.VARIANT_WAVEFRONT, flag, 42, hs.background), want_accum=True)
+    st_w = ctx.stats()
+    assert st_w["variant_used"] == rtw.abi.VARIANT_WAVEFRONT and st_w["n_launches"] > 4
+    assert (wave[1][..., 3] == spp).all()
+    assert st_w["paths"] == st_m["paths"] == W * H * spp and st_w["rays"] == st_m["rays"]
+    for k in ("scatter_diffuse", "scatter_metal", "scatter_dielectric", "emit_hits", "sphere_finalise"):
+        assert st_w[k] == st_m[k], k
+    np.testing.assert_allclose(wave[1][..., :3], mega[1][..., :3], rtol=3e-5, atol=2e-5)
+    diff = np.abs(wave[0].astype(int) - mega[0].astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
 def test_fp32_peak_is_plausible(ctx):
     tf, mhz = ctx.measure_fp32_peak()
     assert 30.0 < tf < 100.0 and mhz > 1000
