@@ -684,7 +684,8 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     rp.n_sblocks = (spp + kBatchSpp - 1) / kBatchSpp;
     if ((uint64_t)rp.n_sblocks * rp.n_tiles > 0xFFFFFFF0ull) return fail(ctx, 1, "too many path batches for one launch");
     rp.n_batches = rp.n_sblocks * rp.n_tiles;
-    rp.service_threshold = 12; rp.steps_per_round = 2;
+    rp.service_threshold = 20; rp.steps_per_round = 2; rp.leaf_threshold = 8;  // tuned on the 485-sphere scene
+    if (const char *e = getenv("RTW_BVH_LEAF")) rp.leaf_threshold = (uint32_t)std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("RTW_BVH_THRESH")) rp.service_threshold = (uint32_t)std::max(1, std::min(32, atoi(e)));
     if (const char *e = getenv("RTW_BVH_STEPS")) rp.steps_per_round = (uint32_t)std::max(1, std::min(64, atoi(e)));
 

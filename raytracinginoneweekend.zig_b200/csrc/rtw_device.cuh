@@ -134,7 +134,7 @@ struct DevRender {
     float4 *accum;                 // width*height, row j = reference scanline j
     unsigned int *tile_counter;    // persistent-kernel work queue (tiles x chunks, or path batches)
     uint32_t n_batches, n_sblocks, batch_spp;  // pooled kernel: batch = one tile x batch_spp samples
-    uint32_t service_threshold, steps_per_round;  // BVH state machine tuning
+    uint32_t service_threshold, steps_per_round, leaf_threshold;  // BVH state machine tuning
     unsigned long long *stats;     // ST_COUNT counters (instrumented build only)
     uint32_t n_tiles, tiles_x, spp_chunk, n_chunks;
 };

@@ -270,10 +270,19 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
             if (alive && !trav) trav = !tv.init(r, sc);
             if (!__any_sync(0xffffffffu, alive)) break;  // pool exhausted and every path finished
         }
-        // ---- traversal phase ----
+        // ---- leaf phase: lanes parked at a leaf wait until enough of them have gathered (or nobody is
+        //      left descending), then test their primitives together ----
+        {
+            const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
+            const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
+            if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
+                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS>(r, sc, 0.001f, cn);
+            }
+        }
+        // ---- interior phase ----
 #pragma unroll 1
         for (uint32_t k = 0; k < rp.steps_per_round; ++k) {
-            if (trav) trav = !tv.template step<STATS>(r, sc, 0.001f, cn);
+            if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, 0.001f, cn);
         }
     }
     if (STATS) cn.flush(rp.stats);

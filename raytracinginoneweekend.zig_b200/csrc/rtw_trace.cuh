@@ -393,46 +393,58 @@ struct BvhTraversal {
         return false;
     }
 
-    // returns true when the traversal is finished
+    __device__ __forceinline__ bool at_leaf() const { return (cur >> 28) != 0u; }
+
+    // one interior visit: both children of `cur` (precondition: !at_leaf()).  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
-        if (!(cur >> 28)) {  // interior: fetch both children (one aligned 64-byte pair), ordered descent
-            const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
-            const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
-            const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
-            const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
-            cn.add(ST_NODE_TESTS, 2);
-            float tl, tr;
-            const bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
-            const bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
-            const uint32_t el = node_ref(L.a, L.b), er = node_ref(R.a, R.b);
-            if (hl && hr) {
-                const bool left_first = tl <= tr;
-                stack[sp++] = left_first ? er : el;  // depth is bounded by the builder (<= kBvhStack)
-                cur = left_first ? el : er;
-            } else if (hl || hr) {
-                cur = hl ? el : er;
-            } else {
-                if (sp == 0) return true;
-                cur = stack[--sp];
-            }
-        }
-        if (cur >> 28) {  // leaf: the only primitive-test site
-            const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const uint32_t slot = at + i;
-                const float4 *pp = reinterpret_cast<const float4 *>(sc.prims_bvh + slot);
-                DevPrim p;
-                p.a = __ldg(pp); p.b = __ldg(pp + 1);
-                float t;
-                if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
-                    const uint32_t id = __ldg(sc.bvh_prim_id + slot);
-                    if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
-                }
-            }
+    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+        const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
+        const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+        const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
+        const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
+        cn.add(ST_NODE_TESTS, 2);
+        float tl, tr;
+        const bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
+        const bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
+        const uint32_t el = node_ref(L.a, L.b), er = node_ref(R.a, R.b);
+        if (hl && hr) {
+            const bool left_first = tl <= tr;
+            stack[sp++] = left_first ? er : el;  // depth is bounded by the builder (<= kBvhStack)
+            cur = left_first ? el : er;
+        } else if (hl || hr) {
+            cur = hl ? el : er;
+        } else {
             if (sp == 0) return true;
             cur = stack[--sp];
         }
+        return false;
+    }
+
+    // one leaf visit (precondition: at_leaf()): the only primitive-test site.  Returns true when finished.
+    template <bool STATS>
+    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+        const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t slot = at + i;
+            const float4 *pp = reinterpret_cast<const float4 *>(sc.prims_bvh + slot);
+            DevPrim p;
+            p.a = __ldg(pp); p.b = __ldg(pp + 1);
+            float t;
+            if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
+                const uint32_t id = __ldg(sc.bvh_prim_id + slot);
+                if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
+            }
+        }
+        if (sp == 0) return true;
+        cur = stack[--sp];
+        return false;
+    }
+
+    // at most one interior visit followed by at most one leaf visit.  Returns true when finished.
+    template <bool STATS>
+    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+        if (!at_leaf() && interior_step<STATS>(r, sc, t_min, cn)) return true;
+        if (at_leaf()) return leaf_step<STATS>(r, sc, t_min, cn);
         return false;
     }
 };

@@ -158,7 +158,16 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_bvh(WfState st, const De
             if (!more && pool_next == pool_end) break;
             continue;
         }
-        if (trav && tv.template step<STATS>(r, sc, 0.001f, cn)) {
+        // leaf phase (gathered: run when >= leaf_threshold lanes are parked at a leaf or nobody descends), then
+        // one interior step
+        bool done = false;
+        const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
+        const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
+        if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
+            if (trav && tv.at_leaf()) done = tv.template leaf_step<STATS>(r, sc, 0.001f, cn);
+        }
+        if (trav && !done && !tv.at_leaf()) done = tv.template interior_step<STATS>(r, sc, 0.001f, cn);
+        if (done) {
             trav = false;
             st.rd[slot].w = tv.h.t;
             st.hit[slot] = tv.h.slot;  // BVH: leaf-order slot
