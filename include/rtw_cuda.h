@@ -236,6 +236,14 @@ int rtw_cuda_resolve_multi(rtw_ctx *ctx, const float *const *d_accums, uint32_t 
                            uint32_t width, uint32_t height, uint32_t spp_total,
                            uint8_t *d_rgb8, void *stream);
 
+/* Single-process multi-GPU form of rtw_cuda_render: `ctxs[i]` live on different devices and hold the SAME
+ * uploaded scene.  Context i traces its share of [spp_begin, spp_end) (first spp mod n contexts take one extra
+ * sample) into its own fp32 buffer; context 0's resolve kernel then reads every buffer through NVLink peer
+ * mappings and sums + resolves in one pass (no separate reduction step), and the image is copied to rgb8_out
+ * (HOST).  Needs peer access between device 0 and the others.  Blocking. */
+int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera *cam,
+                          const rtw_render_params *params, uint8_t *rgb8_out);
+
 /* Parity probes: the closest-hit query `world.hit(r, 0.001, inf, &rec)` of
  * src/main.zig:109 for explicit rays.  precision = 32 (production arithmetic) or 64
  * (same device code instantiated in double: bit-comparable with the reference's f64).

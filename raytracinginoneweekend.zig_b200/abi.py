@@ -82,6 +82,6 @@ class Stats(C.Structure):
 CUDA_SYMBOLS = (
     "rtw_cuda_create", "rtw_cuda_destroy", "rtw_cuda_last_error", "rtw_cuda_abi_version",
     "rtw_cuda_upload_scene", "rtw_cuda_render", "rtw_cuda_accumulate", "rtw_cuda_resolve",
-    "rtw_cuda_resolve_multi", "rtw_cuda_trace_rays", "rtw_cuda_primary_hits", "rtw_cuda_stats",
+    "rtw_cuda_resolve_multi", "rtw_cuda_render_multi", "rtw_cuda_trace_rays", "rtw_cuda_primary_hits", "rtw_cuda_stats",
     "rtw_cuda_measure_fp32_peak",
 )

@@ -804,6 +804,65 @@ int rtw_cuda_render(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params
     return 0;
 }
 
+int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera *cam, const rtw_render_params *p,
+                          uint8_t *rgb8_out) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return fail(nullptr, 1, "no contexts");
+    rtw_ctx *ctx = ctxs[0];
+    if (n_ctx > kMaxResolveBufs) return fail(ctx, 1, "at most %u contexts", kMaxResolveBufs);
+    if (!cam || !p || !rgb8_out) return fail(ctx, 1, "null argument");
+    if (p->variant == RTW_VARIANT_WAVEFRONT) return fail(ctx, 1, "render_multi runs the megakernel variants only");
+    if (p->width == 0 || p->height == 0 || p->spp_end <= p->spp_begin) return fail(ctx, 1, "empty image or sample range");
+    const size_t npx = (size_t)p->width * p->height;
+    const uint32_t spp = p->spp_end - p->spp_begin;
+    const uint32_t spp_total = p->spp_total ? p->spp_total : spp;
+    const float *bufs[kMaxResolveBufs];
+    for (uint32_t i = 0; i < n_ctx; ++i) {
+        rtw_ctx *c = ctxs[i];
+        if (!c) return fail(ctx, 1, "context %u is null", i);
+        for (uint32_t k = 0; k < i; ++k)
+            if (ctxs[k]->device == c->device) return fail(ctx, 1, "contexts %u and %u share device %d", k, i, c->device);
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, 2, "cudaSetDevice(%d) failed", c->device);
+        if (c->accum.n != npx) {
+            if (c->accum.alloc(npx) != cudaSuccess || c->rgb8.alloc(npx * 3) != cudaSuccess) return fail(ctx, 2, "allocation failed on device %d", c->device);
+        }
+        if (cudaMemsetAsync(c->accum.p, 0, npx * sizeof(float4), c->stream) != cudaSuccess) return fail(ctx, 2, "memset failed");
+        rtw_render_params sub = *p;
+        const uint32_t base = spp / n_ctx, extra = spp % n_ctx;
+        sub.spp_begin = p->spp_begin + i * base + std::min(i, extra);
+        sub.spp_end = sub.spp_begin + base + (i < extra ? 1u : 0u);
+        if (int rc = accumulate_impl(c, cam, &sub, reinterpret_cast<float *>(c->accum.p), c->stream, i == 0)) {
+            if (c != ctx) ctx->err = c->err;
+            return rc;
+        }
+        bufs[i] = reinterpret_cast<const float *>(c->accum.p);
+    }
+    for (uint32_t i = 0; i < n_ctx; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        if (cudaStreamSynchronize(ctxs[i]->stream) != cudaSuccess) return fail(ctx, 2, "device %d: kernel failed: %s", ctxs[i]->device, cudaGetErrorString(cudaGetLastError()));
+    }
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 1; i < n_ctx; ++i) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[i]->device));
+        if (!can) return fail(ctx, 3, "device %d cannot map device %d's memory (no peer access)", ctx->device, ctxs[i]->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[i]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, 2, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (int rc = rtw_cuda_resolve_multi(ctx, bufs, n_ctx, p->width, p->height, spp_total, ctx->rgb8.p, ctx->stream)) return rc;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaMemcpyAsync(rgb8_out, ctx->rgb8.p, npx * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.ms_trace = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    ctx->stats.ms_resolve = ms;
+    ctx->stats.n_launches = n_ctx + 1;
+    return 0;
+}
+
 static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_camera *cam, uint32_t width, uint32_t height,
                       uint32_t precision, uint32_t variant_req, uint32_t *prim_id, double *t, double *normal, double *uv) {
     if (!ctx) return fail(nullptr, 1, "ctx is null");

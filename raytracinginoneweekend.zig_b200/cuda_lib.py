@@ -44,6 +44,7 @@ def load(build_if_missing=True):
     L.rtw_cuda_accumulate.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), vp, vp]
     L.rtw_cuda_resolve.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
     L.rtw_cuda_resolve_multi.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    L.rtw_cuda_render_multi.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), vp]
     L.rtw_cuda_trace_rays.argtypes = [vp, C.c_uint32, dp, C.c_uint32, C.c_uint32, u32p, dp, dp, dp]
     L.rtw_cuda_primary_hits.argtypes = [vp, C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         u32p, dp, dp]
@@ -57,6 +58,17 @@ def load(build_if_missing=True):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def render_multi(contexts, cam, params, rgb8=None):
+    """Single-process multi-GPU render: one Context per device, same scene uploaded to each."""
+    H, W = params.height, params.width
+    if rgb8 is None:
+        rgb8 = np.empty((H, W, 3), dtype=np.uint8)
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = contexts[0].L.rtw_cuda_render_multi(arr, len(contexts), C.byref(cam), C.byref(params), rgb8.ctypes.data)
+    contexts[0]._check(rc, "rtw_cuda_render_multi")
+    return rgb8
 
 
 class Context:

@@ -55,6 +55,10 @@ int rtw_host_write_ppm(const char *path, const uint8_t *rgb8, uint32_t width, ui
     return writePpm(path, rgb8, width, height) ? 0 : 1;
 }
 
+int rtw_host_write_png(const char *path, const uint8_t *rgb8, uint32_t width, uint32_t height) {
+    return writePng(path, rgb8, width, height) ? 0 : 1;
+}
+
 // Decode a PNG into caller memory (rgba may be null to query the size).  Returns 0 on success.
 int rtw_host_decode_png(const char *path, uint32_t *width, uint32_t *height, uint8_t *rgba, uint64_t capacity) {
     Image im;

@@ -3,7 +3,7 @@
 // rtw_cuda_render, write the image (PPM, as north_star asks; the reference writes out.png).
 //
 // The reference has no CLI (all parameters are source constants); flags here expose
-// those constants: --scene N --width W --spp S --depth D --seed K --grid G --variant V --asset PATH --out FILE
+// those constants: --scene N --width W --spp S --depth D --seed K --grid G --variant V --gpus N --asset PATH --out FILE(.ppm|.png)
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -17,7 +17,7 @@
 using namespace rtw_host;
 
 int main(int argc, char **argv) {
-    int scene = 6, grid = 3, width = 0, spp = 0, depth = 0, variant = 0, device = 0;
+    int scene = 6, grid = 3, width = 0, spp = 0, depth = 0, variant = 0, device = 0, gpus = 1;
     uint64_t seed = 42;
     std::string asset = "assets/sekaichizu.png", out = "out.ppm", lib = "";
     for (int i = 1; i + 1 < argc; i += 2) {
@@ -30,6 +30,7 @@ int main(int argc, char **argv) {
         else if (k == "--depth") depth = atoi(v);
         else if (k == "--variant") variant = atoi(v);
         else if (k == "--device") device = atoi(v);
+        else if (k == "--gpus") gpus = atoi(v);
         else if (k == "--seed") seed = strtoull(v, nullptr, 10);
         else if (k == "--asset") asset = v;
         else if (k == "--out") out = v;
@@ -51,7 +52,7 @@ int main(int argc, char **argv) {
     void *h = dlopen(lib.c_str(), RTLD_NOW);
     if (!h) { fprintf(stderr, "cannot load %s: %s\n", lib.c_str(), dlerror()); return 1; }
 #define SYM(name) auto name##_ = reinterpret_cast<decltype(&name)>(dlsym(h, #name)); if (!name##_) { fprintf(stderr, "missing symbol %s\n", #name); return 1; }
-    SYM(rtw_cuda_create) SYM(rtw_cuda_destroy) SYM(rtw_cuda_last_error) SYM(rtw_cuda_upload_scene) SYM(rtw_cuda_render) SYM(rtw_cuda_stats)
+    SYM(rtw_cuda_create) SYM(rtw_cuda_destroy) SYM(rtw_cuda_last_error) SYM(rtw_cuda_upload_scene) SYM(rtw_cuda_render) SYM(rtw_cuda_render_multi) SYM(rtw_cuda_stats)
 
     SceneSetup s;
     try { s = makeScene(scene, grid, seed, asset); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return 1; }
@@ -62,22 +63,31 @@ int main(int argc, char **argv) {
     const FlatScene flat = flatten(s.world, 0, 1);
     const rtw_scene_desc desc = flat.desc();
 
-    rtw_ctx *ctx = nullptr;
-    if (rtw_cuda_create_(device, &ctx)) { fprintf(stderr, "rtw_cuda_create: %s\n", rtw_cuda_last_error_(nullptr)); return 1; }
-    if (rtw_cuda_upload_scene_(ctx, &desc)) { fprintf(stderr, "upload: %s\n", rtw_cuda_last_error_(ctx)); return 1; }
+    std::vector<rtw_ctx *> ctxs((size_t)(gpus > 1 ? gpus : 1), nullptr);
+    for (size_t g = 0; g < ctxs.size(); ++g) {
+        if (rtw_cuda_create_(device + (int)g, &ctxs[g])) { fprintf(stderr, "rtw_cuda_create: %s\n", rtw_cuda_last_error_(nullptr)); return 1; }
+        if (rtw_cuda_upload_scene_(ctxs[g], &desc)) { fprintf(stderr, "upload: %s\n", rtw_cuda_last_error_(ctxs[g])); return 1; }
+    }
+    rtw_ctx *ctx = ctxs[0];
     rtw_render_params p{};
     p.width = s.image_width; p.height = s.image_height;
     p.spp_begin = 0; p.spp_end = s.samples_per_pixel; p.spp_total = s.samples_per_pixel;
     p.max_depth = s.max_depth; p.variant = (uint32_t)variant; p.seed = seed;
     p.background[0] = s.background.x; p.background[1] = s.background.y; p.background[2] = s.background.z;
     std::vector<uint8_t> image((size_t)p.width * p.height * 3);
-    if (rtw_cuda_render_(ctx, &cam.c, &p, image.data(), nullptr)) { fprintf(stderr, "render: %s\n", rtw_cuda_last_error_(ctx)); return 1; }
+    const int rc = ctxs.size() > 1 ? rtw_cuda_render_multi_(ctxs.data(), (uint32_t)ctxs.size(), &cam.c, &p, image.data())
+                                   : rtw_cuda_render_(ctx, &cam.c, &p, image.data(), nullptr);
+    if (rc) { fprintf(stderr, "render: %s\n", rtw_cuda_last_error_(ctx)); return 1; }
     rtw_stats st{};
     rtw_cuda_stats_(ctx, &st);
     const double paths = (double)p.width * p.height * s.samples_per_pixel;
     fprintf(stderr, "scene %d: %u prims, %ux%u, %u spp, trace %.2f ms (%.1f Mpaths/s), resolve %.3f ms\n", scene, desc.n_prims,
             p.width, p.height, s.samples_per_pixel, st.ms_trace, paths / (st.ms_trace * 1e3), st.ms_resolve);
-    if (!writePpm(out, image.data(), p.width, p.height)) { fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
-    rtw_cuda_destroy_(ctx);
+    const bool png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;  // the reference writes out.png (main.zig:405)
+    if (!(png ? writePng(out, image.data(), p.width, p.height) : writePpm(out, image.data(), p.width, p.height))) {
+        fprintf(stderr, "cannot write %s\n", out.c_str());
+        return 1;
+    }
+    for (rtw_ctx *c : ctxs) rtw_cuda_destroy_(c);
     return 0;
 }

@@ -130,6 +130,8 @@ struct SceneSetup {
 SceneSetup makeScene(int scene, int grid, uint64_t seed, const std::string &asset);
 
 bool writePpm(const std::string &path, const uint8_t *rgb8, uint32_t width, uint32_t height);
+// 8-bit RGB PNG (what the reference writes: image.writeToFilePath("out.png"), src/main.zig:405), on zlib
+bool writePng(const std::string &path, const uint8_t *rgb8, uint32_t width, uint32_t height);
 bool decodePng(const std::string &path, Image &out, std::string &err);
 
 }  // namespace rtw_host

@@ -193,6 +193,38 @@ bool writePpm(const std::string &path, const uint8_t *rgb8, uint32_t width, uint
     return std::fclose(f) == 0 && ok;
 }
 
+bool writePng(const std::string &path, const uint8_t *rgb8, uint32_t width, uint32_t height) {
+    // filter type 0 on every row, one zlib stream, one IDAT chunk
+    const size_t stride = (size_t)width * 3;
+    std::vector<uint8_t> raw((stride + 1) * height);
+    for (uint32_t y = 0; y < height; ++y) {
+        raw[(stride + 1) * y] = 0;
+        std::memcpy(&raw[(stride + 1) * y + 1], rgb8 + stride * y, stride);
+    }
+    uLongf zlen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    auto put32 = [](uint8_t *p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; };
+    auto chunk = [&](const char *tag, const uint8_t *data, uint32_t len) {
+        uint8_t hdr[8];
+        put32(hdr, len);
+        std::memcpy(hdr + 4, tag, 4);
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, data, len);
+        uint8_t tail[4];
+        put32(tail, (uint32_t)crc);
+        return std::fwrite(hdr, 1, 8, f) == 8 && (len == 0 || std::fwrite(data, 1, len, f) == len) && std::fwrite(tail, 1, 4, f) == 4;
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    uint8_t ihdr[13];
+    put32(ihdr, width); put32(ihdr + 4, height);
+    ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;  // 8-bit, RGB, deflate, adaptive, no interlace
+    bool ok = std::fwrite(sig, 1, 8, f) == 8 && chunk("IHDR", ihdr, 13) && chunk("IDAT", z.data(), (uint32_t)zlen) && chunk("IEND", nullptr, 0);
+    return std::fclose(f) == 0 && ok;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Hittable constructors
 // ------------------------------------------------------------------------------------------------

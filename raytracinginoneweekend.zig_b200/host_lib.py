@@ -30,6 +30,7 @@ def load():
     L.rtw_host_scene_config.argtypes = [C.c_void_p, dp, u32p]
     L.rtw_host_camera_init.argtypes = [dp, dp, dp] + [C.c_double] * 6 + [C.POINTER(abi.Camera)]
     L.rtw_host_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.rtw_host_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.rtw_host_decode_png.argtypes = [C.c_char_p, u32p, u32p, C.c_void_p, C.c_uint64]
     L.rtw_host_random_real01.argtypes = [C.c_uint64, C.c_int, dp]
     _lib = L
@@ -87,6 +88,13 @@ def write_ppm(path, rgb8):
     rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
     rc = load().rtw_host_write_ppm(path.encode(), rgb8.ctypes.data, rgb8.shape[1], rgb8.shape[0])
     if rc:
+        raise IOError(f"cannot write {path}")
+
+
+def write_png(path, rgb8):
+    """8-bit RGB PNG, the format of the reference's out.png (src/main.zig:405)."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    if load().rtw_host_write_png(path.encode(), rgb8.ctypes.data, rgb8.shape[1], rgb8.shape[0]):
         raise IOError(f"cannot write {path}")
 
 

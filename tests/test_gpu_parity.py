@@ -400,6 +400,32 @@ def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, monkeypatc
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+def test_render_multi_sums_peer_buffers_in_the_resolve_kernel(rtw, ctx):
+    """Single-process multi-GPU: each device traces its sample range, device 0's resolve kernel reads the other
+    devices' buffers over NVLink peer mappings.  Must equal the 1-GPU render of the same sample set."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n, 4)
+    hs = rtw.HostScene(1)
+    W, H, spp = 320, 180, 37
+    cam = hs.camera(aspect=W / H)
+    ctx.upload_scene(hs.desc, keep=hs)
+    p = ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, hs.background)
+    one = ctx.render(cam, p)[0]
+    others = [rtw.Context(i) for i in range(1, n)]
+    try:
+        for c in others:
+            c.upload_scene(hs.desc, keep=hs)
+        multi = rtw.render_multi([ctx] + others, cam, p)
+    finally:
+        for c in others:
+            c.close()
+    diff = np.abs(multi.astype(int) - one.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
 def test_fp32_peak_is_plausible(ctx):
     tf, mhz = ctx.measure_fp32_peak()
     assert 30.0 < tf < 100.0 and mhz > 1000

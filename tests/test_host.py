@@ -98,3 +98,15 @@ def test_ppm_writer(rtw, tmp_path):
     rtw.host_lib.write_ppm(path, img)
     raw = open(path, "rb").read()
     assert raw.startswith(b"P6\n7 5\n255\n") and raw[len(b"P6\n7 5\n255\n"):] == img.tobytes()
+
+
+def test_png_writer_round_trips(rtw, tmp_path):
+    """out.png as the reference writes it (src/main.zig:405): Pillow and our own decoder read back the same pixels."""
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    path = str(tmp_path / "out.png")
+    rtw.host_lib.write_png(path, img)
+    assert np.array_equal(np.array(Image.open(path).convert("RGB")), img)
+    back = rtw.host_lib.decode_png(path)
+    assert np.array_equal(back[..., :3], img) and (back[..., 3] == 255).all()
