@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -126,10 +126,11 @@ def run_reference(args, rank):
     }), flush=True)
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, spp=SPP):
     return {"workload": f"reference scene 1 (random spheres, grid half-extent {GRID}, <=40 prims, checker ground, moving "
-                        f"diffuse spheres) {WIDTH}x{HEIGHT}, {SPP} spp per GPU, depth {DEPTH} = BASELINE.json configs[1]",
-            "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP, "spp_total": SPP * n_gpus, "max_depth": DEPTH,
+                        f"diffuse spheres) {WIDTH}x{HEIGHT}, {spp} spp per GPU, depth {DEPTH}"
+                        + (" = BASELINE.json configs[1]" if spp == SPP else " (NOT the baseline spp)"),
+            "width": WIDTH, "height": HEIGHT, "spp_per_gpu": spp, "spp_total": spp * n_gpus, "max_depth": DEPTH,
             "seed": SEED, "partition": f"spp split x{n_gpus} + NCCL reduce to rank 0" if n_gpus > 1 else "single GPU",
             "l2": "flushed between timed iterations (256 MiB write)"}
 
@@ -278,7 +279,7 @@ def main():
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "mrays_per_s": rays_step * args.steps / (ms_total * 1e-3) / 1e6,
             "rays_per_path": rays_step / paths_step, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+            "dtype": "f32", "data": "synthetic", "config": config_dict(world, spp),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "call": "rtw_cuda_upload_scene + rtw_cuda_render (host buffers)" if world == 1

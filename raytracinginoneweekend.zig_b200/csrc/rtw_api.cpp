@@ -298,7 +298,9 @@ int rtw_cuda_create(int device, rtw_ctx **out) {
     ctx = new rtw_ctx();
     ctx->device = device;
     ctx->n_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "stream create failed"); }
+    // A BLOCKING stream on purpose: cudaMemcpy from pageable memory returns once the data is staged, possibly
+    // before the DMA lands; work in a blocking stream is ordered after it, work in a non-blocking stream is not.
+    if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "stream create failed"); }
     for (auto &ev : ctx->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "event create failed"); }
     if (ctx->tile_counter.alloc(1) != cudaSuccess || ctx->stat_counters.alloc(ST_COUNT) != cudaSuccess) {
@@ -902,6 +904,7 @@ static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_ca
         for (size_t k = 0; k < fr.size(); ++k) fr[k] = (float)rays[k];
         CKP(f_rays.upload(fr));
         CKP(f_t.alloc(n)); CKP(f_n.alloc((size_t)n * 3)); CKP(f_uv.alloc((size_t)n * 2));
+        CKP(cudaDeviceSynchronize());  // the pageable H2D copies above must have landed
         CKP(launch_probe(variant, ctx->scene, n, f_rays.p, d_id.p, f_t.p, f_n.p, f_uv.p, st));
         CKP(cudaStreamSynchronize(st));
         std::vector<float> ht(n), hn((size_t)n * 3), hu((size_t)n * 2);
@@ -925,6 +928,7 @@ static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_ca
             CKP(d_rays.upload(hr));
         }
         CKP(d_t.alloc(n)); CKP(d_n.alloc((size_t)n * 3)); CKP(d_uv.alloc((size_t)n * 2));
+        CKP(cudaDeviceSynchronize());  // the pageable H2D copies above must have landed
         CKP(launch_ref_probe((int)precision, variant, ctx->raw, n, rays ? d_rays.p : nullptr, rays ? nullptr : &rc_cam, width,
                              height, d_id.p, d_t.p, d_n.p, d_uv.p, st));
         CKP(cudaStreamSynchronize(st));
