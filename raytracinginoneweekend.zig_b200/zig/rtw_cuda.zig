@@ -82,6 +82,8 @@ pub extern "c" fn rtw_cuda_abi_version() u32;
 pub extern "c" fn rtw_cuda_upload_scene(ctx: *Ctx, scene: *const SceneDesc) c_int;
 pub extern "c" fn rtw_cuda_render(ctx: *Ctx, cam: *const Camera, params: *const RenderParams, rgb8_out: [*]u8, accum_out: ?[*]f32) c_int;
 
+pub extern "c" fn rtw_cuda_render_multi(ctxs: [*]const ?*Ctx, n_ctx: u32, cam: *const Camera, params: *const RenderParams, rgb8_out: [*]u8) c_int;
+
 pub const Error = error{ CudaUnavailable, SceneRejected, RenderFailed };
 
 /// The reference's hot path is infallible (`hit`/`scatter` return bool); only setup can fail, so the
