@@ -26,7 +26,9 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    # Never rebuild implicitly when the library exists: under torchrun N ranks load it at once, and on the GPU
+    # box the prebuilt in-tree .so is the artefact under test.  __graft_entry__.build() does the real build.
+    if build_if_missing and (not os.path.exists(build.CUDA_LIB) or os.environ.get("RTW_REBUILD") == "1"):
         build.build_cuda()
     if not os.path.exists(build.CUDA_LIB):
         raise RtwCudaError(f"{build.CUDA_LIB} is missing: run __graft_entry__.build() (no CPU fallback exists)")

@@ -19,7 +19,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    build.build_host()
+    if not os.path.exists(build.HOST_LIB) or os.environ.get("RTW_REBUILD") == "1":
+        build.build_host()
     L = C.CDLL(build.HOST_LIB)
     dp, u32p = C.POINTER(C.c_double), C.POINTER(C.c_uint32)
     L.rtw_host_last_error.restype = C.c_char_p

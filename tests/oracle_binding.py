@@ -16,8 +16,9 @@ LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 def build(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_capi.cpp", "rtw_oracle.hpp", "Makefile")]
     srcs.append(os.path.join(ROOT, "include", "rtw_cuda.h"))
-    stale = force or not os.path.exists(LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    # rebuild when missing (or when asked): never implicitly under torchrun / on the GPU box
+    stale = force or not os.path.exists(LIB_PATH) or (os.environ.get("RTW_REBUILD") == "1" and any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs))
     if stale:
         subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
     return LIB_PATH
