@@ -96,6 +96,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank):
     """The reference's CPU implementation of the path (oracle port), all host threads, same config."""
     if rank != 0:
@@ -106,7 +113,7 @@ def run_reference(args, rank):
     hs = rtw_b200.HostScene(1, grid=GRID, seed=SEED)
     osc = ob.OracleScene.from_desc(hs.desc, keep=hs)
     cam = hs.camera(aspect=WIDTH / HEIGHT)
-    nt = ob.num_threads()
+    nt = host_threads()  # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host core
     spp_step = 4  # bounded sample of the 500-spp frame: cost is exactly linear in spp
     for _ in range(args.warmup):
         osc.render(cam, WIDTH, HEIGHT, 1, DEPTH, hs.background, seed=1, precision=64, nthreads=nt, want_rgb8=False)
@@ -295,7 +302,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_binding as ob
             osc = ob.OracleScene.from_desc(hs.desc, keep=hs)
-            nt = ob.num_threads()
+            nt = host_threads()
             cspp = 12
             r = osc.render(cam, WIDTH, HEIGHT, cspp, DEPTH, hs.background, seed=5, precision=64, nthreads=nt, want_rgb8=False)
             r1 = osc.render(cam, WIDTH // 4, HEIGHT // 4, 8, DEPTH, hs.background, seed=5, precision=64, nthreads=1,
