@@ -181,25 +181,36 @@ Box3d leaf_box(const rtw_scene_desc *s, const rtw_prim &p) {
 }
 
 // Compose an instance chain (innermost index `x`) into object = A*world + t, A = Ry.
-DevXform compose_chain(const rtw_scene_desc *s, int x) {
-    // collect outermost-first
-    std::vector<int> chain;
+struct XformD {
+    double c = 1.0, s = 0.0, t[3] = {0, 0, 0};
+    // world = A^T (object - t)
+    void to_world(const double o[3], double w[3]) const {
+        const double x = o[0] - t[0], y = o[1] - t[1], z = o[2] - t[2];
+        w[0] = c * x + s * z; w[1] = y; w[2] = -s * x + c * z;
+    }
+};
+XformD compose_chain_d(const rtw_scene_desc *s, int x) {
+    std::vector<int> chain;  // outermost first
     for (int k = x; k >= 0; k = s->xforms[k].outer) chain.push_back(k);
     std::reverse(chain.begin(), chain.end());
-    double c = 1.0, sn = 0.0, t[3] = {0, 0, 0};  // p_obj = A p + t
+    XformD r;
     for (int k : chain) {
         const rtw_xform &xf = s->xforms[k];
         if (xf.kind == RTW_XFORM_TRANSLATE) {  // p <- p - offset
-            for (int a = 0; a < 3; ++a) t[a] -= xf.v[a];
+            for (int a = 0; a < 3; ++a) r.t[a] -= xf.v[a];
         } else {  // p <- R p with R: x' = c x - s z, z' = s x + c z   (hittable.zig:563-564)
             const double s2 = xf.v[0], c2 = xf.v[1];
-            const double nc = c2 * c - s2 * sn, ns = s2 * c + c2 * sn;
-            const double tx = c2 * t[0] - s2 * t[2], tz = s2 * t[0] + c2 * t[2];
-            c = nc; sn = ns; t[0] = tx; t[2] = tz;
+            const double nc = c2 * r.c - s2 * r.s, ns = s2 * r.c + c2 * r.s;
+            const double tx = c2 * r.t[0] - s2 * r.t[2], tz = s2 * r.t[0] + c2 * r.t[2];
+            r.c = nc; r.s = ns; r.t[0] = tx; r.t[2] = tz;
         }
     }
+    return r;
+}
+DevXform compose_chain(const rtw_scene_desc *s, int x) {
+    const XformD r = compose_chain_d(s, x);
     DevXform d{};
-    d.c = (float)c; d.s = (float)sn; d.tx = (float)t[0]; d.ty = (float)t[1]; d.tz = (float)t[2];
+    d.c = (float)r.c; d.s = (float)r.s; d.tx = (float)r.t[0]; d.ty = (float)r.t[1]; d.tz = (float)r.t[2];
     return d;
 }
 
@@ -224,8 +235,6 @@ int validate(rtw_ctx *ctx, const rtw_scene_desc *s) {
         if (p.material >= s->n_materials) return fail(ctx, 1, "prim %u: material %u out of range", i, p.material);
         if (p.xform < -1 || p.xform >= (int)s->n_xforms) return fail(ctx, 1, "prim %u: xform %d out of range", i, p.xform);
         if (p.kind == RTW_PRIM_MOVING_SPHERE && p.v[7] == p.v[6]) return fail(ctx, 1, "prim %u: time1 == time0", i);
-        if ((p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE) && p.xform >= 0)
-            return fail(ctx, 1, "prim %u: instanced spheres are not supported", i);
     }
     for (uint32_t i = 0; i < s->n_materials; ++i) {
         const rtw_material &m = s->materials[i];
@@ -338,13 +347,38 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     ctx->have_scene = false;
     const uint32_t n = s->n_prims;
 
+    // Instanced spheres (Translate / RotateY around a sphere): a rigid transform keeps a sphere a sphere, so they
+    // are lowered to world-space spheres; the chain is kept only for the texture coordinates (getSphereUv works on
+    // the object-space normal, hittable.zig:127).  `wprims` = the prims with such centres moved to world space.
+    std::vector<rtw_prim> wprims(s->prims, s->prims + n);
+    for (uint32_t i = 0; i < n; ++i) {
+        rtw_prim &p = wprims[i];
+        if (p.xform < 0 || (p.kind != RTW_PRIM_SPHERE && p.kind != RTW_PRIM_MOVING_SPHERE)) continue;
+        const XformD x = compose_chain_d(s, p.xform);
+        x.to_world(&s->prims[i].v[0], &p.v[0]);
+        if (p.kind == RTW_PRIM_MOVING_SPHERE) x.to_world(&s->prims[i].v[3], &p.v[3]);
+    }
     // reference point for big spheres: centroid of the centres of everything that is not big
     double cen[3] = {0, 0, 0};
     uint32_t ncen = 0;
     std::vector<Box3d> boxes(n);
     for (uint32_t i = 0; i < n; ++i) {
-        boxes[i] = leaf_box(s, s->prims[i]);
-        const rtw_prim &p = s->prims[i];
+        {
+            const rtw_prim &wp = wprims[i];
+            if (wp.xform >= 0 && (wp.kind == RTW_PRIM_SPHERE || wp.kind == RTW_PRIM_MOVING_SPHERE)) {
+                rtw_prim q = wp;
+                q.xform = -1;  // already in world space: exact box instead of the box of a rotated box ...
+                boxes[i] = leaf_box(s, q);
+                // ... padded: the reference-order fp32 probe intersects in OBJECT space, so its hit points carry the
+                // rounding of the rotated ray (~1e-7 |o|) and may fall a hair outside the exact world-space box
+                double mag = 1.0;
+                for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(boxes[i].mn[a]), std::fabs(boxes[i].mx[a])));
+                for (int a = 0; a < 3; ++a) { boxes[i].mn[a] -= 4e-6 * mag; boxes[i].mx[a] += 4e-6 * mag; }
+            } else {
+                boxes[i] = leaf_box(s, s->prims[i]);
+            }
+        }
+        const rtw_prim &p = wprims[i];
         if (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius) continue;
         for (int a = 0; a < 3; ++a) cen[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
         ++ncen;
@@ -359,16 +393,29 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     std::map<int, int> xform_slot;
     std::vector<RawPrim> raw(n);
     std::vector<RawXform> chains;
+    auto xform_slot_of = [&](int x) {
+        auto it = xform_slot.find(x);
+        if (it == xform_slot.end()) {
+            xforms.push_back(compose_chain(s, x));
+            it = xform_slot.emplace(x, (int)xforms.size() - 1).first;
+        }
+        return it->second;
+    };
     for (uint32_t i = 0; i < n; ++i) {
-        const rtw_prim &p = s->prims[i];
+        const rtw_prim &p = wprims[i];
         DevPrim d{};
         prim_mat[i] = p.material;
         uint32_t meta = 0;
+        uint32_t sphere_xf = 0;  // xform slot + 1 of an instanced sphere (uv only)
+        if (p.xform >= 0 && (p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE)) {
+            sphere_xf = (uint32_t)xform_slot_of(p.xform) + 1u;
+            if (sphere_xf > 0xFFFu) return fail(ctx, 1, "too many distinct instance chains on spheres (max 4095)");
+        }
         if (p.kind == RTW_PRIM_SPHERE) {
             d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
             d.b = make_float4(0.f, 0.f, 0.f, 0.f);
             meta = PK_SPHERE;
-            if (p.v[3] >= kBigSphereRadius && bigs.size() < 0xFFFFFEu) {
+            if (p.v[3] >= kBigSphereRadius && bigs.size() < 0xFFEu) {
                 // q = point of the sphere surface nearest the scene's centre of interest
                 double dir[3] = {cen[0] - p.v[0], cen[1] - p.v[1], cen[2] - p.v[2]};
                 double len = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
@@ -402,24 +449,16 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             meta = PK_SPHERE;
         } else {
             d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
-            int slot = -1;
-            if (p.xform >= 0) {
-                auto it = xform_slot.find(p.xform);
-                if (it == xform_slot.end()) {
-                    xforms.push_back(compose_chain(s, p.xform));
-                    it = xform_slot.emplace(p.xform, (int)xforms.size() - 1).first;
-                }
-                slot = it->second;
-            }
+            const int slot = p.xform >= 0 ? xform_slot_of(p.xform) : -1;
             d.b = make_float4((float)p.v[4], bits_to_float((uint32_t)slot), 0.f, 0.f);
             meta = p.kind == RTW_PRIM_XY_RECT ? PK_XY : p.kind == RTW_PRIM_XZ_RECT ? PK_XZ : PK_YZ;
         }
-        d.b.w = bits_to_float(meta);
+        d.b.w = bits_to_float(meta | (sphere_xf << 20));
         flat[i] = d;
 
-        RawPrim &r = raw[i];
+        RawPrim &r = raw[i];  // the probe keeps the reference's object-space fields + nested chain
         r.kind = p.kind; r.material = p.material;
-        std::memcpy(r.v, p.v, sizeof r.v);
+        std::memcpy(r.v, s->prims[i].v, sizeof r.v);
         r.chain_begin = (uint32_t)chains.size();
         std::vector<RawXform> tmp;
         for (int x = p.xform; x >= 0; x = s->xforms[x].outer) {
@@ -434,7 +473,9 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     }
 
     // ---- BVH ------------------------------------------------------------------------------------------
-    BvhResult bvh = build_bvh(boxes, 4);
+    uint32_t leaf_max = 4;
+    if (const char *e = getenv("RTW_BVH_LEAF_MAX")) leaf_max = (uint32_t)std::max(1, std::min(15, atoi(e)));  // 4-bit count in node refs
+    BvhResult bvh = build_bvh(boxes, leaf_max);
     if (bvh.depth > (uint32_t)64) return fail(ctx, 2, "BVH depth %u exceeds the traversal stack", bvh.depth);
     std::vector<DevPrim> leaf_order(n);
     for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
@@ -449,7 +490,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             if (p.kind == RTW_PRIM_SPHERE) {
                 uint32_t meta;
                 std::memcpy(&meta, &flat[i].b.w, 4);
-                ((meta >> 8) ? big_ids : stat_ids).push_back(i);  // big_ids in the same order as `bigs`
+                (((meta >> 8) & 0xFFFu) ? big_ids : stat_ids).push_back(i);  // big_ids in the same order as `bigs`
             } else if (p.kind == RTW_PRIM_MOVING_SPHERE) mov_ids.push_back(i);
             else rect_ids.push_back(i);
         }
@@ -487,7 +528,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         };
         // sphere centre of prim i at time t (f64)
         auto centre_at = [&](uint32_t i, double t, double c[3]) {
-            const rtw_prim &p = s->prims[i];
+            const rtw_prim &p = wprims[i];
             if (p.kind == RTW_PRIM_SPHERE) { c[0] = p.v[0]; c[1] = p.v[1]; c[2] = p.v[2]; return p.v[3]; }
             const double u = (t - p.v[6]) / (p.v[7] - p.v[6]);
             for (int a = 0; a < 3; ++a) c[a] = p.v[a] + (p.v[3 + a] - p.v[a]) * u;

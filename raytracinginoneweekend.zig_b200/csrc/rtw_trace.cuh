@@ -104,7 +104,7 @@ __device__ __forceinline__ bool sphere_test(const Ray &r, float add, float inv_a
     if (discp < 0.0f) return false;
     cn.add(ST_SPHERE_ROOTS);
     float c;
-    const uint32_t big = __float_as_uint(p.b.w) >> 8;
+    const uint32_t big = (__float_as_uint(p.b.w) >> 8) & 0xFFFu;
     if (big) {
         // |o-c|^2 - r^2 about a reference point q on the surface: no 1e6 - 1e6 cancellation for the
         // r=1000 ground sphere of main.zig:172.
@@ -119,7 +119,7 @@ __device__ __forceinline__ bool sphere_test(const Ray &r, float add, float inv_a
     const float sq = sqrt_approx(add * discp);
     const float bq = -bp;
     const float q = bq + copysignf(sq, bq);
-    const float t0 = __fdividef(c, q), t1 = q * inv_a;
+    const float t0 = c * rcp_approx(q), t1 = q * inv_a;
     const float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
     float root = lo;
     if (root < t_min || t_max < root) {
@@ -211,7 +211,7 @@ __device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, flo
     const float sq = sqrt_approx(add * discp);
     const float bq = -bp;
     const float q = bq + copysignf(sq, bq);
-    const float t0 = __fdividef(c, q), t1 = q * inv_a;
+    const float t0 = c * rcp_approx(q), t1 = q * inv_a;
     float root = fminf(t0, t1);
     if (root < t_min || t_max < root) {
         root = fmaxf(t0, t1);
@@ -483,6 +483,15 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
         s.onx = (s.px - cx) * inv_r; s.ony = (s.py - cy) * inv_r; s.onz = (s.pz - cz) * inv_r;
         s.is_sphere = true;
         s.u = 0.0f; s.v = 0.0f;
+        const uint32_t xf = __float_as_uint(p.b.w) >> 20;
+        if (xf) {  // instanced sphere: getSphereUv sees the OBJECT-space normal (hittable.zig:127 inside Translate/RotateY)
+            const DevXform x = sc.xforms[xf - 1];
+            const float ux = fmaf(x.c, s.onx, -x.s * s.onz), uz = fmaf(x.s, s.onx, x.c * s.onz);
+            const float pi = 3.14159265358979323846f;
+            s.u = (atan2f(-uz, ux) + pi) / (2.0f * pi);
+            s.v = acosf(fminf(fmaxf(-s.ony, -1.0f), 1.0f)) / pi;
+            s.is_sphere = false;  // uv already final
+        }
     } else {
         // object-space rect: outward normal is the +axis (hittable.zig:295-301), uv = normalised
         // in-plane coordinates (hittable.zig:288-289)

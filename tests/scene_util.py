@@ -68,11 +68,11 @@ class DescBuilder:
         self.prims.append(p)
         return len(self.prims) - 1
 
-    def sphere(self, c, r, mat):
-        return self._prim(abi.PRIM_SPHERE, mat, -1, [*c, r])
+    def sphere(self, c, r, mat, xform=-1):
+        return self._prim(abi.PRIM_SPHERE, mat, xform, [*c, r])
 
-    def moving_sphere(self, c0, c1, t0, t1, r, mat):
-        return self._prim(abi.PRIM_MOVING_SPHERE, mat, -1, [*c0, *c1, t0, t1, r])
+    def moving_sphere(self, c0, c1, t0, t1, r, mat, xform=-1):
+        return self._prim(abi.PRIM_MOVING_SPHERE, mat, xform, [*c0, *c1, t0, t1, r])
 
     def rect(self, kind, a0, a1, b0, b1, k, mat, xform=-1):
         return self._prim(kind, mat, xform, [a0, a1, b0, b1, k])
@@ -100,7 +100,7 @@ class DescBuilder:
         return d
 
 
-def random_scene(rng, n_spheres=40, n_moving=20, n_rects=20, n_boxes=3, extent=10.0):
+def random_scene(rng, n_spheres=40, n_moving=20, n_rects=20, n_boxes=3, extent=10.0, n_inst_spheres=6):
     """Mixed random scene: static + moving spheres, axis rects, instanced boxes, a big ground sphere."""
     b = DescBuilder()
     mats = [b.diffuse(b.solid((0.5, 0.5, 0.5))), b.metal((0.8, 0.8, 0.8), 0.1), b.glass(1.5),
@@ -120,6 +120,14 @@ def random_scene(rng, n_spheres=40, n_moving=20, n_rects=20, n_boxes=3, extent=1
         t = b.translate(rng.uniform(-extent, extent, 3))
         r = b.rotate_y(rng.uniform(-90, 90), outer=t)
         b.box((0, 0, 0), rng.uniform(0.5, 3, 3), mats[rng.integers(0, 4)], xform=r)
+    for k in range(n_inst_spheres):  # Translate(RotateY(sphere)) and Translate(RotateY(moving sphere))
+        t = b.translate(rng.uniform(-extent, extent, 3))
+        r = b.rotate_y(rng.uniform(-180, 180), outer=t)
+        c = rng.uniform(-2, 2, 3)
+        if k % 2 == 0:
+            b.sphere(c, rng.uniform(0.3, 1.5), mats[rng.integers(0, 4)], xform=r)
+        else:
+            b.moving_sphere(c, c + rng.uniform(-1, 1, 3), 0.0, 1.0, rng.uniform(0.3, 1.0), mats[rng.integers(0, 4)], xform=r)
     return b.build()
 
 

@@ -426,6 +426,40 @@ def test_render_multi_sums_peer_buffers_in_the_resolve_kernel(rtw, ctx):
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+def test_instanced_spheres_uv_and_image(rtw, oracle, ctx, earth_rgba):
+    """Translate(RotateY(sphere)) with an image texture: production uv follows the OBJECT-space normal like the
+    reference (getSphereUv inside the instance, hittable.zig:127,583-593), and the rendered image matches."""
+    b = scene_util.DescBuilder()
+    earth = b.diffuse(b.image(earth_rgba))
+    grey = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    t = b.translate((1.5, 0.5, -1.0))
+    r = b.rotate_y(70.0, outer=t)
+    b.sphere((0, 0, 0), 2.0, earth, xform=r)
+    b.sphere((0, -1002, 0), 1000.0, grey)
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    cam = rtw.camera_init((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.0)
+    rng = np.random.default_rng(3)
+    rays = scene_util.random_rays(rng, 20000, extent=3.0)
+    oid, ot, on, ouv = osc.trace_rays(rays, 64)
+    for variant in (1, 2):
+        gid, gt, gn, guv = ctx.trace_rays(rays, 0, variant)
+        ok = (gid == oid) & (oid == 0)
+        assert (gid != oid).mean() < 1e-3 and ok.sum() > 1000
+        du = np.abs(guv[ok, 0] - ouv[ok, 0]); du = np.minimum(du, 1 - du)
+        assert du.max() < 2e-4 and np.abs(guv[ok, 1] - ouv[ok, 1]).max() < 2e-3
+        for prec in (32, 64):
+            a = ctx.trace_rays(rays, prec, variant)
+            o = osc.trace_rays(rays, prec)
+            assert np.array_equal(a[0], o[0]) and np.array_equal(a[1], o[1]) and np.array_equal(a[2], o[2])
+    W, H, spp = 120, 80, 128
+    ref = osc.render(cam, W, H, spp * 8, 50, (0.7, 0.8, 1.0), seed=5, precision=64, nthreads=max(2, oracle.num_threads()))["accum"] / (spp * 8)
+    acc = ctx.render(cam, ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, (0.7, 0.8, 1.0)), want_accum=True)[1][..., :3] / spp
+    rel = np.abs(acc.mean((0, 1)) - ref.mean((0, 1))) / ref.mean((0, 1))
+    assert (rel < 0.005).all(), rel
+
+
 def test_fp32_peak_is_plausible(ctx):
     tf, mhz = ctx.measure_fp32_peak()
     assert 30.0 < tf < 100.0 and mhz > 1000
