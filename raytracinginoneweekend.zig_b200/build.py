@@ -48,7 +48,33 @@ def _deps(d, exts):
     return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(exts)]
 
 
+class _BuildLock:
+    """Serialises in-tree builds across processes (torchrun starts N ranks at once)."""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(OUT, exist_ok=True)
+        self.f = open(os.path.join(OUT, ".build.lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def build_cuda(force=False, verbose=False, extra=()):
+    with _BuildLock():
+        return _build_cuda(force, verbose, extra)
+
+
+def build_host(force=False, verbose=False):
+    with _BuildLock():
+        return _build_host(force, verbose)
+
+
+def _build_cuda(force=False, verbose=False, extra=()):
     os.makedirs(OUT, exist_ok=True)
     hdrs = _deps(CSRC, (".h", ".cuh")) + [os.path.join(ROOT, "include", "rtw_cuda.h"), os.path.abspath(__file__)]
     units = [
@@ -72,7 +98,7 @@ def build_cuda(force=False, verbose=False, extra=()):
     return CUDA_LIB
 
 
-def build_host(force=False, verbose=False):
+def _build_host(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
     srcs = _deps(HOST, (".cpp",))
     hdrs = _deps(HOST, (".hpp", ".h")) + [os.path.join(ROOT, "include", "rtw_cuda.h"), os.path.abspath(__file__)]
