@@ -223,11 +223,16 @@ __device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, flo
 }
 
 // does the ray (t >= 0) possibly touch the bounding sphere?  line test + "entirely behind" test
-__device__ __forceinline__ bool bound_hit(const Ray &r, float inv_a, const float4 b) {
+// `reach` = best.t * |d|: the bound is also skipped when even its nearest point lies beyond the current
+// closest hit (the big spheres — the ground — are tested first so that this culls)
+__device__ __forceinline__ bool bound_hit(const Ray &r, float inv_a, const float4 b, float reach) {
     float ox, oy, oz, bp;
     const float d = sphere_disc(r, inv_a, b.x, b.y, b.z, b.w, ox, oy, oz, bp);
     const float oo = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
-    return d >= 0.0f && !(bp > 0.0f && oo > b.w);
+    // origin outside the bound and either the bound is behind, or |oc| - R > reach, i.e. |oc|^2 > (reach + R)^2
+    const float R = sqrt_approx(b.w) * 1.00001f;
+    const float lim = fmaf(reach, fmaf(2.0f, R, reach), b.w * 1.00002f);
+    return d >= 0.0f && !(oo > b.w && (bp > 0.0f || oo > lim));
 }
 
 template <bool STATS>
@@ -256,23 +261,10 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
                                                 const DevScene &sc, float t_min, Counters<STATS> &cn) {
     const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
     const float inv_a = rcp_approx(add);
+    const float len = sqrt_approx(add) * 1.00001f;  // |d|, rounded up: best.t * len = reach of the current closest hit
     FlatBest best{__int_as_float(0x7f800000), kMiss};
     const uint32_t *ids = reinterpret_cast<const uint32_t *>(s + L.off_ids);
 
-    // ---- static sphere groups ----
-    {
-        const float4 *gp = s + L.off_sph, *const ge = gp + 5 * L.n_sph_groups;
-        const uint32_t *ip = ids;
-#pragma unroll 1
-        for (; gp < ge; gp += 5, ip += 4) {
-            if (active) cn.add(ST_SPHERE_TESTS);  // the bound is a sphere test too
-            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
-            if (active) cn.add(ST_SPHERE_TESTS, 4);
-            const uint4 id = *reinterpret_cast<const uint4 *>(ip);
-            flat_static_pair<STATS>(r, add, inv_a, gp[1], gp[2], id.x, id.y, active, t_min, best, cn);
-            flat_static_pair<STATS>(r, add, inv_a, gp[3], gp[4], id.z, id.w, active, t_min, best, cn);
-        }
-    }
     // ---- big static spheres: c term about the reference point ----
     {
         const float4 *sp = s + L.off_big;
@@ -293,6 +285,20 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
             }
         }
     }
+    // ---- static sphere groups ----
+    {
+        const float4 *gp = s + L.off_sph, *const ge = gp + 5 * L.n_sph_groups;
+        const uint32_t *ip = ids;
+#pragma unroll 1
+        for (; gp < ge; gp += 5, ip += 4) {
+            if (active) cn.add(ST_SPHERE_TESTS);  // the bound is a sphere test too
+            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0], best.t * len))) continue;
+            if (active) cn.add(ST_SPHERE_TESTS, 4);
+            const uint4 id = *reinterpret_cast<const uint4 *>(ip);
+            flat_static_pair<STATS>(r, add, inv_a, gp[1], gp[2], id.x, id.y, active, t_min, best, cn);
+            flat_static_pair<STATS>(r, add, inv_a, gp[3], gp[4], id.z, id.w, active, t_min, best, cn);
+        }
+    }
     // ---- moving sphere groups: centre(time) = cb + vel*time (hittable.zig:219-221) ----
     {
         const float4 *gp = s + L.off_mov, *const ge = gp + 9 * L.n_mov_groups;
@@ -300,7 +306,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
 #pragma unroll 1
         for (; gp < ge; gp += 9, ip += 4) {
             if (active) cn.add(ST_SPHERE_TESTS);
-            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0]))) continue;
+            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0], best.t * len))) continue;
             if (active) { cn.add(ST_SPHERE_TESTS, 4); cn.add(ST_MOVING_TESTS, 4); }
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
 #pragma unroll
