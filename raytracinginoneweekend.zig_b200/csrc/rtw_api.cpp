@@ -723,8 +723,18 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     if (chunk == 0) chunk = 1;
     rp.spp_chunk = chunk;
     rp.n_chunks = spp ? (spp + chunk - 1) / chunk : 0;
-    rp.batch_spp = kBatchSpp;
-    rp.n_sblocks = (spp + kBatchSpp - 1) / kBatchSpp;
+    // Batch = one 8x4 tile x batch_spp samples.  Large frames use 64 samples per batch; small frames shrink the
+    // batch so that every resident warp still gets >= ~24 batches (otherwise the launch is all tail: the
+    // reference's own 600x400x50 frame would be 1.4 batches per warp).
+    uint32_t batch_spp = kBatchSpp;
+    if (spp > 0) {
+        const uint64_t warps = (uint64_t)grid * 4, want = warps * 24;
+        const uint64_t sblocks_wanted = (want + rp.n_tiles - 1) / rp.n_tiles;
+        if (sblocks_wanted > 1) batch_spp = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(kBatchSpp, spp / sblocks_wanted));
+        if (const char *e = getenv("RTW_BATCH_SPP")) batch_spp = (uint32_t)std::max(1, std::min(4096, atoi(e)));
+    }
+    rp.batch_spp = batch_spp;
+    rp.n_sblocks = (spp + batch_spp - 1) / batch_spp;
     if ((uint64_t)rp.n_sblocks * rp.n_tiles > 0xFFFFFFF0ull) return fail(ctx, 1, "too many path batches for one launch");
     rp.n_batches = rp.n_sblocks * rp.n_tiles;
     rp.service_threshold = 20; rp.steps_per_round = 2; rp.leaf_threshold = 8;  // tuned on the 485-sphere scene
