@@ -582,8 +582,32 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                 } else { mov.push_back(dummy); mov.push_back(zero4); ids.push_back(0); }
             }
         }
-        for (uint32_t i : rect_ids) { rect.push_back(flat[i].a); rect.push_back(flat[i].b); ids.push_back(i); }
-        while (ids.size() & 3) ids.push_back(0);
+        // rect runs: equal (xform slot, orientation), in order of first appearance
+        std::vector<float4> runs;
+        {
+            std::vector<std::pair<int, uint32_t>> keys;  // (xform slot, kind)
+            std::vector<std::vector<uint32_t>> members;
+            for (uint32_t i : rect_ids) {
+                int slot; uint32_t meta;
+                std::memcpy(&slot, &flat[i].b.y, 4); std::memcpy(&meta, &flat[i].b.w, 4);
+                const std::pair<int, uint32_t> key{slot, meta & 0xFFu};
+                size_t k = 0;
+                for (; k < keys.size(); ++k) if (keys[k] == key) break;
+                if (k == keys.size()) { keys.push_back(key); members.emplace_back(); }
+                members[k].push_back(i);
+            }
+            for (size_t k = 0; k < keys.size(); ++k) {
+                const uint32_t first = (uint32_t)(rect.size() / 2);
+                for (uint32_t i : members[k]) {
+                    rect.push_back(flat[i].a);
+                    rect.push_back(make_float4(flat[i].b.x, bits_to_float(i), 0.f, 0.f));
+                }
+                float4 rd;
+                const uint32_t w[4] = {(uint32_t)(keys[k].first + 1), keys[k].second, first, (uint32_t)members[k].size()};
+                std::memcpy(&rd, w, 16);
+                runs.push_back(rd);
+            }
+        }
         fl.n_sphere_real = (uint32_t)(stat_ids.size() + big_ids.size() + mov_ids.size());
         fl.n_sph_groups = (uint32_t)sgroups.size(); fl.n_big = (uint32_t)big_ids.size();
         fl.n_mov_groups = (uint32_t)mgroups.size(); fl.n_rect = (uint32_t)rect_ids.size();
@@ -591,11 +615,14 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         fl.off_big = fl.off_sph + (uint32_t)sph.size();
         fl.off_mov = fl.off_big + (uint32_t)big.size();
         fl.off_rect = fl.off_mov + (uint32_t)mov.size();
-        fl.off_ids = fl.off_rect + (uint32_t)rect.size();
+        fl.off_runs = fl.off_rect + (uint32_t)rect.size();
+        fl.n_runs = (uint32_t)runs.size();
+        fl.off_ids = fl.off_runs + (uint32_t)runs.size();
         blob.insert(blob.end(), sph.begin(), sph.end());
         blob.insert(blob.end(), big.begin(), big.end());
         blob.insert(blob.end(), mov.begin(), mov.end());
         blob.insert(blob.end(), rect.begin(), rect.end());
+        blob.insert(blob.end(), runs.begin(), runs.end());
         const size_t at = blob.size();
         blob.resize(at + ids.size() / 4);
         if (!ids.empty()) std::memcpy(&blob[at], ids.data(), ids.size() * 4);

@@ -78,15 +78,18 @@ struct DevPerlin {
 //   sph groups : 5 x float4  = bound (cx, cy, cz, R^2) + 4 members (cx, cy, cz, r^2)
 //   big        : 1 x float4  (cx, cy, cz, r^2) per big static sphere; DevBigSphere i in scene.bigs
 //   mov groups : 9 x float4  = bound + 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}
-//   rect       : 2 x float4 as DevPrim
-//   ids        : uint32 prim id per member slot, in the order sph | big | mov | rect
+//   rect       : 2 x float4 per rect: (a0, a1, b0, b1), (k, bits(prim id), -, -), sorted into RUNS of equal
+//                (instance transform, orientation) so the object-space ray is set up once per run and the
+//                inner loop is specialised per orientation and branch-free
+//   runs       : uint4 per run: (xform slot + 1 or 0, PK_XY/XZ/YZ, first rect, count)
+//   ids        : uint32 prim id per member slot, in the order sph | big | mov
 // Unused member slots have r^2 = -1 (never hit).
 struct FlatLayout {
     uint32_t n_sph_groups, n_big, n_mov_groups, n_rect;
     uint32_t off_sph, off_big, off_mov, off_rect, off_ids;
     uint32_t total_f4;
     uint32_t n_sphere_real;  // for the event counters
-    uint32_t pad;
+    uint32_t n_runs, off_runs, pad0, pad1, pad2;
 };
 
 struct DevScene {

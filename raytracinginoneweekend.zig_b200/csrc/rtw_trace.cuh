@@ -256,6 +256,28 @@ __device__ __forceinline__ void flat_static_pair(const Ray &r, float add, float 
     }
 }
 
+// A run of rects sharing orientation and instance transform: t = (k - o_k)/d_k (hittable.zig:279), in-plane
+// bounds inclusive (hittable.zig:283), range [t_min, best] inclusive, ties to the larger prim id.
+template <bool STATS>
+__device__ __forceinline__ void rect_run(float ok, float dk, float oa, float da, float ob, float db, const float4 *rp,
+                                         uint32_t count, bool active, float t_min, FlatBest &best, Counters<STATS> &cn) {
+    const float inv = rcp_approx(dk);  // dk == 0: t = +-inf or NaN
+#pragma unroll 2
+    for (uint32_t i = 0; i < count; ++i) {
+        const float4 a = rp[2 * i], b = rp[2 * i + 1];
+        const float t = (b.x - ok) * inv;
+        const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
+        // rejection written exactly as the reference does (hittable.zig:280,285): a NaN t (origin on the plane of a
+        // parallel ray) fails every comparison and is therefore NOT rejected there either
+        const bool hit = active && !(t < t_min || t > best.t || pa < a.x || pa > a.y || pb < a.z || pb > a.w);
+        const uint32_t id = __float_as_uint(b.y);
+        if (STATS) { if (hit) cn.add(ST_RECT_ACCEPTS); }
+        const bool take = hit && (t < best.t || best.id == kMiss || id > best.id);
+        best.t = take ? t : best.t;
+        best.id = take ? id : best.id;
+    }
+}
+
 template <bool STATS>
 __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const float4 *s, const FlatLayout &L,
                                                 const DevScene &sc, float t_min, Counters<STATS> &cn) {
@@ -318,33 +340,23 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
             }
         }
     }
-    // ---- rects: the instance transform is recomputed only when the (warp-uniform) xform id changes ----
+    // ---- rects: runs of equal (instance transform, orientation) ----
     {
-        const float4 *rp = s + L.off_rect;
-        const uint32_t *rid = ids + 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u) + 4 * L.n_mov_groups;
-        int cur = -1;
-        float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
-        for (uint32_t i = 0; i < L.n_rect; ++i) {
-            DevPrim p;
-            p.a = rp[2 * i]; p.b = rp[2 * i + 1];
-            if (active) cn.add(ST_RECT_TESTS);
-            const int xi = __float_as_int(p.b.y);
-            if (xi != cur) {
-                cur = xi;
-                if (xi >= 0) {
-                    if (active) cn.add(ST_XFORM_APPS);
-                    const DevXform x = sc.xforms[xi];
-                    ox = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; oy = r.oy + x.ty; oz = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
-                    dx = fmaf(x.c, r.dx, -x.s * r.dz); dy = r.dy; dz = fmaf(x.s, r.dx, x.c * r.dz);
-                } else {
-                    ox = r.ox; oy = r.oy; oz = r.oz; dx = r.dx; dy = r.dy; dz = r.dz;
-                }
+        const uint4 *runs = reinterpret_cast<const uint4 *>(s + L.off_runs);
+        for (uint32_t q = 0; q < L.n_runs; ++q) {
+            const uint4 run = runs[q];
+            float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+            if (run.x) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
+                if (active) cn.add(ST_XFORM_APPS);
+                const DevXform x = sc.xforms[run.x - 1u];
+                o[0] = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; o[1] = r.oy + x.ty; o[2] = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
+                d[0] = fmaf(x.c, r.dx, -x.s * r.dz); d[2] = fmaf(x.s, r.dx, x.c * r.dz);
             }
-            float t;
-            if (active && rect_test_os(__float_as_uint(p.b.w) & 0xFFu, ox, oy, oz, dx, dy, dz, p, t_min, best.t, t)) {
-                cn.add(ST_RECT_ACCEPTS);
-                flat_consider(best, t, rid[i]);
-            }
+            const float4 *rp = s + L.off_rect + 2 * run.z;
+            if (active) cn.add(ST_RECT_TESTS, run.w);
+            if (run.y == PK_XY) rect_run<STATS>(o[2], d[2], o[0], d[0], o[1], d[1], rp, run.w, active, t_min, best, cn);
+            else if (run.y == PK_XZ) rect_run<STATS>(o[1], d[1], o[0], d[0], o[2], d[2], rp, run.w, active, t_min, best, cn);
+            else rect_run<STATS>(o[0], d[0], o[1], d[1], o[2], d[2], rp, run.w, active, t_min, best, cn);
         }
     }
     return Hit{best.t, best.id};
