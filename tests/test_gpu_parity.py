@@ -460,6 +460,31 @@ def test_instanced_spheres_uv_and_image(rtw, oracle, ctx, earth_rgba):
     assert (rel < 0.005).all(), rel
 
 
+def test_million_sphere_scene(rtw, oracle, ctx):
+    """BASELINE.json configs[3] at full primitive count (10^6 spheres, BVH): production-arithmetic primary-hit ids
+    against the f64 oracle (its own BVH, validated against its linear scan elsewhere), f64 reference-order probe
+    bit-exact, and the size-independent render properties."""
+    hs = rtw.HostScene(rtw.host_lib.SCENE_SPHERE_FIELD, grid=500)
+    assert hs.desc.n_prims > 990000
+    ctx.upload_scene(hs.desc, keep=hs)
+    st = ctx.stats()
+    assert st["bvh_depth"] <= 64 and st["bvh_nodes"] > hs.desc.n_prims
+    osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
+    W, H = 160, 90
+    cam = hs.camera(aspect=W / H)
+    oid, ot, on = osc.primary_hits(cam, W, H, 64, use_bvh=True)
+    gid, gt, gn = ctx.primary_hits(cam, W, H, 0, rtw.abi.VARIANT_MEGA_BVH)
+    assert (gid != oid).mean() <= 5e-4, (gid != oid).sum()
+    g64 = ctx.primary_hits(cam, W, H, 64, rtw.abi.VARIANT_MEGA_BVH)
+    assert np.array_equal(g64[0], oid) and np.array_equal(g64[1], ot) and np.array_equal(g64[2], on)
+    assert 0.2 < (oid != MISS).mean() <= 1.0
+    p = ctx.params(320, 180, 0, 8, 8, 50, 0, rtw.abi.FLAG_COUNT_EVENTS, 42, hs.background)
+    rgb, acc = ctx.render(cam, p, want_accum=True)
+    s2 = ctx.stats()
+    assert s2["variant_used"] == rtw.abi.VARIANT_MEGA_BVH and s2["paths"] == 320 * 180 * 8
+    assert (acc[..., 3] == 8).all() and np.isfinite(acc).all() and acc[..., :3].max() <= 8.0 + 1e-3
+
+
 def test_fp32_peak_is_plausible(ctx):
     tf, mhz = ctx.measure_fp32_peak()
     assert 30.0 < tf < 100.0 and mhz > 1000
