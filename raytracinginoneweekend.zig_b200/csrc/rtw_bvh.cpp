@@ -2,9 +2,14 @@
 #include "rtw_bvh.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <cstdlib>
 #include <limits>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace rtw {
 namespace {
@@ -63,15 +68,33 @@ BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
             cen[3 * (size_t)i + a] = 0.5f * (pb[i].mn[a] + pb[i].mx[a]);
         }
 
-    struct Task { uint32_t node, lo, hi, depth; };
-    std::vector<Task> stack;
-    stack.push_back({0, 0, n, 1});
+    // Nodes are preallocated (a binary tree over n leaves has < 2n nodes; +2 for the root slot and its pad) and pairs
+    // are handed out from per-thread chunks of an atomic cursor, so subtrees built by one thread stay contiguous.
+    unsigned n_threads = 1;
+    constexpr uint32_t kSerialBelow = 8192;  // subtrees smaller than this are finished by the thread that reaches them
+    if (n >= 4 * kSerialBelow) {
+        n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char *e = getenv("RTW_BUILD_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
+    }
+    const uint32_t chunk_pairs = n_threads > 1 ? 512u : 1u;
+    out.nodes.resize(2 * (size_t)n + 2 + (size_t)n_threads * 2 * chunk_pairs);
+    std::atomic<uint32_t> node_cursor{2};
+    std::atomic<uint32_t> max_depth{1};
     constexpr int kBins = 16;
     constexpr uint32_t kSahDepthLimit = 36;  // deeper than this: median splits (log2 n more levels at most)
-    while (!stack.empty()) {
-        const Task tk = stack.back();
-        stack.pop_back();
-        out.depth = std::max(out.depth, tk.depth);
+
+    struct Task { uint32_t node, lo, hi, depth; };
+    struct Alloc { uint32_t next = 0, end = 0; };
+    auto alloc_pair = [&](Alloc &al) {
+        if (al.next == al.end) { al.next = node_cursor.fetch_add(2 * chunk_pairs); al.end = al.next + 2 * chunk_pairs; }
+        const uint32_t at = al.next;
+        al.next += 2;
+        return at;
+    };
+    // Splits one node; returns false for a leaf, else fills the two child tasks.
+    auto split = [&](const Task &tk, Alloc &al, Task &lt, Task &rt) -> bool {
+        uint32_t d = max_depth.load(std::memory_order_relaxed);
+        while (tk.depth > d && !max_depth.compare_exchange_weak(d, tk.depth)) {}
         Aabb bounds, cb;
         bounds.reset(); cb.reset();
         for (uint32_t i = tk.lo; i < tk.hi; ++i) {
@@ -84,7 +107,7 @@ BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
         }
         const uint32_t count = tk.hi - tk.lo;
         auto make_leaf = [&]() { write_node(out.nodes[tk.node], bounds, tk.lo, count); };
-        if (count == 1) { make_leaf(); continue; }
+        if (count == 1) { make_leaf(); return false; }
 
         // binned SAH
         int best_axis = -1, best_split = -1;
@@ -126,7 +149,7 @@ BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
             }
         }
         const float leaf_cost = bounds.half_area() * (float)count;
-        if (count <= max_leaf && (best_axis < 0 || best_cost + bounds.half_area() >= leaf_cost)) { make_leaf(); continue; }
+        if (count <= max_leaf && (best_axis < 0 || best_cost + bounds.half_area() >= leaf_cost)) { make_leaf(); return false; }
 
         uint32_t mid;
         if (best_axis >= 0) {
@@ -148,13 +171,69 @@ BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
             std::nth_element(out.order.begin() + tk.lo, out.order.begin() + mid, out.order.begin() + tk.hi,
                              [&](uint32_t x, uint32_t y) { return cen[3 * (size_t)x + ax] < cen[3 * (size_t)y + ax]; });
         }
-        const uint32_t left = (uint32_t)out.nodes.size();
-        out.nodes.emplace_back();
-        out.nodes.emplace_back();
+        const uint32_t left = alloc_pair(al);
         write_node(out.nodes[tk.node], bounds, left, 0);
-        stack.push_back({left, tk.lo, mid, tk.depth + 1});
-        stack.push_back({left + 1, mid, tk.hi, tk.depth + 1});
+        lt = Task{left, tk.lo, mid, tk.depth + 1};
+        rt = Task{left + 1, mid, tk.hi, tk.depth + 1};
+        return true;
+    };
+    auto build_serial = [&](const Task &root, Alloc &al) {  // depth-first, private stack
+        std::vector<Task> st{root};
+        while (!st.empty()) {
+            const Task tk = st.back();
+            st.pop_back();
+            Task l, r;
+            if (split(tk, al, l, r)) { st.push_back(l); st.push_back(r); }
+        }
+    };
+
+    if (n_threads <= 1) {
+        Alloc al;
+        build_serial(Task{0, 0, n, 1}, al);
+    } else {
+        // shared queue of large subtrees; a worker finishes small subtrees itself
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<Task> queue{Task{0, 0, n, 1}};
+        unsigned busy = 0;
+        bool done = false;
+        auto worker = [&]() {
+            Alloc al;
+            for (;;) {
+                Task tk;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return done || !queue.empty(); });
+                    if (queue.empty()) return;
+                    tk = queue.back();
+                    queue.pop_back();
+                    ++busy;
+                }
+                if (tk.hi - tk.lo < kSerialBelow) {
+                    build_serial(tk, al);
+                } else {
+                    Task l, r;
+                    if (split(tk, al, l, r)) {
+                        std::lock_guard<std::mutex> lk(mu);
+                        queue.push_back(l);
+                        queue.push_back(r);
+                        cv.notify_all();
+                    }
+                }
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    --busy;
+                    if (busy == 0 && queue.empty()) { done = true; cv.notify_all(); }
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+        for (auto &t : pool) t.join();
     }
+    out.depth = max_depth.load();
+    // unused tail of the preallocation (chunks leave holes: harmless, never referenced) is trimmed to the cursor
+    out.nodes.resize(std::min<size_t>(out.nodes.size(), node_cursor.load()));
     out.root_is_leaf = out.nodes[0].b != 0;
     // keep reference order inside each leaf (ties then resolve like the linear scan without id lookups)
     for (const BvhNode &nd : out.nodes)
