@@ -483,7 +483,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     // ---- shared-memory image for the flat scan: segmented by kind, small spheres in groups of four --------
     FlatLayout fl{};
     std::vector<float4> blob;
-    {
+    if (n <= kFlatHardMax) {  // big scenes never run the flat scan: skip the (costly) grouping
         std::vector<uint32_t> stat_ids, mov_ids, big_ids, rect_ids;
         for (uint32_t i = 0; i < n; ++i) {
             const rtw_prim &p = s->prims[i];
