@@ -1,18 +1,20 @@
 // rtw_kernels.cu — production kernels (fp32, FMA contraction on), sm_100a.
 //
-//   k_megakernel<VARIANT,STATS>  K1: replaces the loop nest src/main.zig:382-394 and everything below it
-//   k_resolve                    K4: replaces src/main.zig:395-400 (average, sqrt, clamp, x256 -> u8, row flip),
+//   k_megakernel_pooled<FLAT,STATS>  K1 for scenes of <= 64 primitives: flat scan out of shared memory
+//   k_megakernel_bvh<STATS>          K1 for larger scenes: BVH traversal as a per-lane state machine
+//   k_megakernel<VARIANT,STATS>      K1, deterministic form (lane owns a pixel; RTW_FLAG_DETERMINISTIC)
+//        all three replace the loop nest src/main.zig:382-394 and everything below it
+//   k_resolve / k_resolve4           K4: replaces src/main.zig:395-400 (average, sqrt, clamp, x256 -> u8, row flip),
 //                                    optionally summing several (peer-mapped) accumulation buffers first
-//   k_probe                      production-arithmetic closest-hit probe (parity instrument)
-//   k_ffma_peak                  FP32 roofline denominator, measured on the device
+//   k_probe<VARIANT>                 production-arithmetic closest-hit probe (parity instrument)
+//   k_ffma_peak                      FP32 roofline denominator, measured on the device
 //
-// Megakernel design.  The work is embarrassingly parallel, FP32/issue bound, with two sources of
-// SIMT inefficiency: paths of very different length (1..50 rays) and per-ray divergence in traversal
-// and material code.  The kernel is persistent: a grid of (#SMs x resident CTAs) CTAs pulls work items
-// (an 8x4 pixel tile x a chunk of samples) from an atomic queue.  Inside a warp, lane = pixel; each
-// lane runs a regenerate-on-terminate loop: when its path ends it immediately starts the next sample
-// of its own pixel, so lanes stay busy until the chunk's samples run out; per-pixel sums stay in
-// registers and are flushed once per work item.
+// Megakernel design.  The work is embarrassingly parallel and FP32/issue bound, with two sources of SIMT
+// inefficiency: paths of very different length (1..50 rays) and per-ray divergence in traversal and material
+// code.  All kernels are persistent: a grid of (#SMs x resident CTAs) CTAs pulls batches (an 8x4 pixel tile x a block
+// of samples) from an atomic queue.  In the pooled kernels a warp owns the batch as a pool of path indices: whenever
+// lanes finish their paths they are handed the next indices (ballot + popc prefix), so no lane waits for a longer
+// neighbour, and a finished path is added to the frame with one vector reduction.  DESIGN.md §3 has the ncu history.
 #include <cuda_runtime.h>
 
 #include "rtw_kernels.h"
