@@ -549,7 +549,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             R = R * (1.0 + 1e-5) + 1e-6;  // fp32 evaluation slack
             const float cf[3] = {(float)cen[0], (float)cen[1], (float)cen[2]};
             for (int a = 0; a < 3; ++a) R += std::fabs((double)cf[a] - cen[a]);
-            return make_float4(cf[0], cf[1], cf[2], (float)(R * R * (1.0 + 1e-6)));
+            return make_float4(cf[0], cf[1], cf[2], (float)(R * (1.0 + 1e-6)));  // the radius, not its square
         };
         const auto sgroups = make_groups(stat_ids), mgroups = make_groups(mov_ids);
         std::vector<float4> sph, big, mov, rect;

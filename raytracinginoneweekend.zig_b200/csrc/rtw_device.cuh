@@ -75,7 +75,7 @@ struct DevPerlin {
 // Shared-memory image of a small scene for the flat scan, as one blob of float4 (offsets in float4
 // units).  Primitives are SEGMENTED BY KIND and small spheres are packed into spatial GROUPS of four
 // behind a bounding sphere, so that a whole warp can skip a group with one vote:
-//   sph groups : 5 x float4  = bound (cx, cy, cz, R^2) + 4 members (cx, cy, cz, r^2)
+//   sph groups : 5 x float4  = bound (cx, cy, cz, R) + 4 members (cx, cy, cz, r^2)
 //   big        : 1 x float4  (cx, cy, cz, r^2) per big static sphere; DevBigSphere i in scene.bigs
 //   mov groups : 9 x float4  = bound + 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}
 //   rect       : 2 x float4 per rect: (a0, a1, b0, b1), (k, bits(prim id), -, -), sorted into RUNS of equal

@@ -225,14 +225,15 @@ __device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, flo
 // does the ray (t >= 0) possibly touch the bounding sphere?  line test + "entirely behind" test
 // `reach` = best.t * |d|: the bound is also skipped when even its nearest point lies beyond the current
 // closest hit (the big spheres — the ground — are tested first so that this culls)
+// b = (centre, R): the radius itself is stored (R^2 is one multiply away, R would be a MUFU)
 __device__ __forceinline__ bool bound_hit(const Ray &r, float inv_a, const float4 b, float reach) {
     float ox, oy, oz, bp;
-    const float d = sphere_disc(r, inv_a, b.x, b.y, b.z, b.w, ox, oy, oz, bp);
+    const float rr = b.w * b.w;
+    const float d = sphere_disc(r, inv_a, b.x, b.y, b.z, rr, ox, oy, oz, bp);
     const float oo = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
     // origin outside the bound and either the bound is behind, or |oc| - R > reach, i.e. |oc|^2 > (reach + R)^2
-    const float R = sqrt_approx(b.w) * 1.00001f;
-    const float lim = fmaf(reach, fmaf(2.0f, R, reach), b.w * 1.00002f);
-    return d >= 0.0f && !(oo > b.w && (bp > 0.0f || oo > lim));
+    const float lim = fmaf(reach, fmaf(2.0f, b.w, reach), rr);
+    return d >= 0.0f && !(oo > rr && (bp > 0.0f || oo > lim));
 }
 
 template <bool STATS>
