@@ -724,6 +724,10 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     rp.spp_begin = p->spp_begin; rp.spp_end = p->spp_end;
     rp.max_depth = p->max_depth;
     rp.seed_lo = (uint32_t)p->seed; rp.seed_hi = (uint32_t)(p->seed >> 32);
+    for (uint32_t i = 0; i < 10; ++i) {
+        rp.philox_keys[2 * i] = rp.seed_lo + i * 0x9E3779B9u;
+        rp.philox_keys[2 * i + 1] = rp.seed_hi + i * 0xBB67AE85u;
+    }
     rp.bg_r = (float)p->background[0]; rp.bg_g = (float)p->background[1]; rp.bg_b = (float)p->background[2];
     rp.inv_wm1 = (float)(1.0 / ((double)p->width - 1.0)); rp.inv_hm1 = (float)(1.0 / ((double)p->height - 1.0));
     rp.accum = reinterpret_cast<float4 *>(d_accum);

@@ -132,6 +132,7 @@ struct DevRender {
     uint32_t spp_begin, spp_end;
     uint32_t max_depth;
     uint32_t seed_lo, seed_hi;
+    uint32_t philox_keys[20];      // Philox4x32-10 round keys: (seed_lo + i*0x9E3779B9, seed_hi + i*0xBB67AE85), i = 0..9
     float bg_r, bg_g, bg_b;
     float inv_wm1, inv_hm1;        // 1/(W-1), 1/(H-1)  (main.zig:390-391)
     float4 *accum;                 // width*height, row j = reference scanline j

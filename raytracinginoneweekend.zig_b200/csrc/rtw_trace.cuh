@@ -20,15 +20,15 @@ namespace rtw {
 // block 0 = camera ray, block b>=1 = bounce b.  Every draw of a (pixel, sample, bounce) is a pure
 // function of its indices, so any partition of the samples over threads/GPUs gives the same paths.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint32_t k0, uint32_t k1) {
-    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// The ten round keys (key + i * Weyl constants) are the same for every call of a launch: the host expands them once
+// into DevRender::philox_keys, so a round is 2 IMAD.WIDE + 2 LOP3 with a constant-bank operand and no key arithmetic.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const uint32_t (&keys)[20]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
         const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0);
-        k0 += W0;
-        k1 += W1;
+        ctr = make_uint4(hi1 ^ ctr.y ^ keys[2 * i], lo1, hi0 ^ ctr.w ^ keys[2 * i + 1], lo0);
     }
     return ctr;
 }
@@ -640,7 +640,7 @@ __device__ __forceinline__ float2 sample_unit_disk(float u1, float u2) {  // ran
 // 24-bit uniforms sliced out of its 128 bits.
 __device__ __forceinline__ Ray camera_ray(const DevCamera &cam, const DevRender &rp, uint32_t pixel, uint32_t i,
                                           uint32_t j, uint32_t sample) {
-    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.seed_lo, rp.seed_hi);
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.philox_keys);
     const float ju = u01_24(rn.x), jv = u01_24(rn.y);
     const float l1 = u01_24(rn.z), l2 = u01_24(rn.w);
     const float tm = u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8));
@@ -675,7 +675,7 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, R
         L.x = fmaf(beta.x, e.x, L.x); L.y = fmaf(beta.y, e.y, L.y); L.z = fmaf(beta.z, e.z, L.z);
         return false;
     }
-    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.seed_lo, rp.seed_hi);
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.philox_keys);
     float ndx, ndy, ndz;
     if (m.kind == 0u) {  // diffuse material.zig:44-52
         cn.add(ST_SC_DIFFUSE);
