@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 1u
+#define RTW_ABI_VERSION 2u
 
 /* ---- primitives: the leaf variants of `Hittable` (src/rtw/hittable.zig:22-33) -------- */
 enum {
@@ -150,6 +150,13 @@ enum {
     RTW_VARIANT_WAVEFRONT = 3  /* per-bounce ray queues, compaction between bounces           */
 };
 
+/* Who built the BVH of the uploaded scene (rtw_stats.bvh_builder).  Scenes of >= 65536 primitives build on
+ * the device; the environment variable RTW_BVH_BUILDER=sah|lbvh overrides the choice. */
+enum {
+    RTW_BVH_BUILDER_SAH  = 0, /* host: binned surface-area heuristic                          */
+    RTW_BVH_BUILDER_LBVH = 1  /* device: Morton order + parallel radix tree                   */
+};
+
 typedef struct rtw_render_params {
     uint32_t width;
     uint32_t height;
@@ -198,6 +205,9 @@ typedef struct rtw_stats {
     uint32_t variant_used;
     uint32_t bvh_nodes;
     uint32_t bvh_depth;
+    double   ms_bvh_build;     /* BVH part of ms_upload                                         */
+    uint32_t bvh_builder;      /* RTW_BVH_BUILDER_*                                             */
+    uint32_t reserved0;
 } rtw_stats;
 
 typedef struct rtw_ctx rtw_ctx;

@@ -1,7 +1,7 @@
 """ctypes mirror of include/rtw_cuda.h (field for field; checked by tests/test_abi.py)."""
 import ctypes as C
 
-RTW_ABI_VERSION = 1
+RTW_ABI_VERSION = 2
 RTW_MISS = 0xFFFFFFFF
 
 PRIM_SPHERE, PRIM_MOVING_SPHERE, PRIM_XY_RECT, PRIM_XZ_RECT, PRIM_YZ_RECT = range(5)
@@ -11,6 +11,7 @@ TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = range(4)
 VARIANT_AUTO, VARIANT_MEGA_FLAT, VARIANT_MEGA_BVH, VARIANT_WAVEFRONT = range(4)
 FLAG_COUNT_EVENTS = 1
 FLAG_DETERMINISTIC = 2
+BVH_BUILDER_SAH, BVH_BUILDER_LBVH = range(2)
 
 
 class Prim(C.Structure):
@@ -72,7 +73,8 @@ class Stats(C.Structure):
         "scatter_dielectric", "emit_hits", "tex_checker", "tex_image", "tex_noise", "nan_pixels")] + [
         ("ms_trace", C.c_double), ("ms_resolve", C.c_double), ("ms_upload", C.c_double),
         ("n_launches", C.c_uint32), ("variant_used", C.c_uint32), ("bvh_nodes", C.c_uint32),
-        ("bvh_depth", C.c_uint32)]
+        ("bvh_depth", C.c_uint32), ("ms_bvh_build", C.c_double), ("bvh_builder", C.c_uint32),
+        ("reserved0", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -16,11 +16,13 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rtw_cuda.h"
 #include "rtw_bvh.h"
 #include "rtw_kernels.h"
+#include "rtw_lbvh.h"
 
 using namespace rtw;
 
@@ -30,6 +32,7 @@ namespace {
 constexpr double kBigSphereRadius = 64.0;
 // Scenes up to this many primitives default to the warp-uniform flat scan (measured crossover).
 constexpr uint32_t kFlatAutoMax = 64;
+constexpr uint32_t kLbvhAutoMin = 1u << 16;  // scenes at least this large build their BVH on the device
 constexpr uint32_t kFlatHardMax = 6000;  // the shared-memory image must stay under ~200 KB
 constexpr uint32_t kBatchSpp = 64;       // pooled kernel: a batch = one 8x4 tile x 64 samples = 2048 paths
 
@@ -63,6 +66,42 @@ struct DevBuf {
     }
 };
 
+
+// Splits [0, n) into fixed chunks (independent of the machine, so chunk-ordered reductions are reproducible) and runs
+// fn(chunk, lo, hi) over them on a few threads when the scene is large; small scenes stay on the calling thread.
+constexpr uint32_t kChunk = 1u << 15;
+inline uint32_t n_chunks_of(uint32_t n) { return (n + kChunk - 1) / kChunk; }
+template <class F>
+void for_chunks(uint32_t n, F &&fn) {
+    const uint32_t nc = n_chunks_of(n);
+    unsigned nt = 1;
+    if (nc >= 4) {
+        nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char *e = getenv("RTW_BUILD_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        nt = std::min<unsigned>(nt, nc);
+    }
+    auto run = [&](unsigned t) {
+        for (uint32_t c = t; c < nc; c += nt) fn(c, c * kChunk, std::min(n, (c + 1) * kChunk));
+    };
+    if (nt <= 1) { run(0); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(run, t);
+    run(0);
+    for (auto &t : pool) t.join();
+}
+
+// RTW_UPLOAD_TRACE=1: per-stage wall times of rtw_cuda_upload_scene on stderr
+struct Laps {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const bool on = getenv("RTW_UPLOAD_TRACE") != nullptr;
+    void lap(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rtw upload] %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 }  // namespace
 
 struct rtw_ctx {
@@ -89,6 +128,10 @@ struct rtw_ctx {
     std::vector<cudaTextureObject_t> image_tex;
     DevScene scene{};
     RawScene raw{};
+    // host copy kept for the reference-order probe (object-space f64 fields + nested chains), uploaded on first use
+    std::vector<rtw_prim> host_prims;  // instanced spheres already moved to world space ...
+    std::vector<std::pair<uint32_t, std::array<double, 10>>> host_inst_orig;  // ... their object-space fields
+    std::vector<rtw_xform> host_xforms;
     uint32_t n_prims = 0;
     bool root_is_leaf = false;
 
@@ -339,6 +382,125 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
     delete ctx;
 }
 
+// Device-side BVH build (rtw_lbvh.cu) into ctx->nodes / bvh_prim_id / prims_bvh; ctx->prims_flat must be uploaded.
+// Primitives whose box dwarfs the spread of the rest would drag every Morton ancestor up to scene size, so they get
+// their own small SAH subtree (host) and the two subtrees meet under a new root:
+//   nodes: [0] root  [1] pad  [2] big subtree root  [3] Morton subtree root  [4..] big pairs, then Morton pairs
+//   slots: [0, nb) big primitives in their leaf order, [nb, n) the rest in Morton order
+// *built = false (and rc 0) when the result would not fit the traversal (stack depth) or the input is degenerate.
+static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, uint32_t leaf_max, uint32_t *n_nodes,
+                               uint32_t *depth, bool *built) {
+    *built = false;
+    const uint32_t n = (uint32_t)boxes.size();
+    std::vector<float> fb(6 * (size_t)n);
+    struct Part {
+        float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};  // centroids
+        float bmn[3] = {INFINITY, INFINITY, INFINITY}, bmx[3] = {-INFINITY, -INFINITY, -INFINITY};  // boxes
+        bool finite = true;
+        std::vector<uint32_t> big, small;
+        void merge(const Part &o) {
+            for (int a = 0; a < 3; ++a) {
+                cmn[a] = std::min(cmn[a], o.cmn[a]); cmx[a] = std::max(cmx[a], o.cmx[a]);
+                bmn[a] = std::min(bmn[a], o.bmn[a]); bmx[a] = std::max(bmx[a], o.bmx[a]);
+            }
+            finite = finite && o.finite;
+        }
+    };
+    std::vector<Part> parts(n_chunks_of(n));
+    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+        Part pt;
+        for (uint32_t i = lo; i < hi; ++i) {
+            float *b = &fb[6 * (size_t)i];
+            box_to_f32(boxes[i], b);
+            for (int a = 0; a < 3; ++a) {
+                const float c = 0.5f * (b[a] + b[3 + a]);
+                if (!(std::fabs(c) <= 3e38f)) pt.finite = false;
+                pt.cmn[a] = std::min(pt.cmn[a], c); pt.cmx[a] = std::max(pt.cmx[a], c);
+                pt.bmn[a] = std::min(pt.bmn[a], b[a]); pt.bmx[a] = std::max(pt.bmx[a], b[3 + a]);
+            }
+        }
+        parts[chunk] = std::move(pt);
+    });
+    Part all;
+    for (const Part &pt : parts) all.merge(pt);
+    if (!all.finite) return 0;  // non-finite boxes: leave them to the host builder
+    const float spread = std::max(all.cmx[0] - all.cmn[0], std::max(all.cmx[1] - all.cmn[1], all.cmx[2] - all.cmn[2]));
+    // second pass: split off the big ones, Morton grid over the centroids of what is left
+    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+        Part &pt = parts[chunk];
+        pt = Part{};
+        for (uint32_t i = lo; i < hi; ++i) {
+            const float *b = &fb[6 * (size_t)i];
+            const float ext = std::max(b[3] - b[0], std::max(b[4] - b[1], b[5] - b[2]));
+            if (ext > 0.125f * spread) { pt.big.push_back(i); continue; }
+            pt.small.push_back(i);
+            for (int a = 0; a < 3; ++a) {
+                const float c = 0.5f * (b[a] + b[3 + a]);
+                pt.cmn[a] = std::min(pt.cmn[a], c); pt.cmx[a] = std::max(pt.cmx[a], c);
+            }
+        }
+    });
+    constexpr uint32_t kMaxBig = 4096;
+    std::vector<uint32_t> big_ids, small_ids;
+    small_ids.reserve(n);
+    Part rest;
+    for (const Part &pt : parts) {
+        rest.merge(pt);
+        big_ids.insert(big_ids.end(), pt.big.begin(), pt.big.end());
+        small_ids.insert(small_ids.end(), pt.small.begin(), pt.small.end());
+    }
+    if (big_ids.size() > kMaxBig) return 0;  // no clear size gap: a job for the SAH builder
+    const uint32_t nb = (uint32_t)big_ids.size(), ns = (uint32_t)small_ids.size();
+    if (ns < 2 || ns <= leaf_max) return 0;
+    const float *all_mn = all.bmn, *all_mx = all.bmx, *smn = rest.cmn, *smx = rest.cmx;
+    const float sext[3] = {smx[0] - smn[0], smx[1] - smn[1], smx[2] - smn[2]};
+
+    BvhResult big;
+    std::vector<BvhNode> head;
+    std::vector<uint32_t> big_order(nb);
+    uint32_t root_slot = 0, pair_base = 2;
+    if (nb) {
+        std::vector<Box3d> bb(nb);
+        for (uint32_t k = 0; k < nb; ++k) bb[k] = boxes[big_ids[k]];
+        big = build_bvh(bb, leaf_max);
+        for (uint32_t k = 0; k < nb; ++k) big_order[k] = big_ids[big.order[k]];
+        const uint32_t B = (uint32_t)big.nodes.size();  // [0] root, [1] pad, pairs from 2
+        head.assign((size_t)B + 2, BvhNode{0, 0, 0, 0, 0, 0, 0, 0});
+        head[0] = BvhNode{all_mn[0], all_mn[1], all_mn[2], 2u, all_mx[0], all_mx[1], all_mx[2], 0u};
+        auto moved = [](BvhNode nd) { if (nd.b == 0) nd.a += 2; return nd; };  // interior: its pair moves up by two
+        head[2] = moved(big.nodes[0]);
+        for (uint32_t k = 2; k < B; ++k) head[k + 2] = moved(big.nodes[k]);
+        root_slot = 3;
+        pair_base = B + 2;
+    } else {
+        head.assign(2, BvhNode{0, 0, 0, 0, 0, 0, 0, 0});
+    }
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<float> d_boxes;
+    DevBuf<uint32_t> d_ids;
+    struct Scope { DevBuf<float> &a; DevBuf<uint32_t> &b; ~Scope() { a.release(); b.release(); } } scope{d_boxes, d_ids};
+    CK(d_boxes.upload(fb));
+    CK(d_ids.upload(small_ids));
+    CK(ctx->nodes.alloc((size_t)pair_base + 2 * (size_t)(ns - 1)));
+    CK(ctx->bvh_prim_id.alloc(n));
+    CK(ctx->prims_bvh.alloc(n));
+    CK(cudaMemcpy(ctx->nodes.p, head.data(), head.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    if (nb) CK(cudaMemcpy(ctx->bvh_prim_id.p, big_order.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
+    LbvhInfo info;
+    CK(build_lbvh(d_boxes.p, d_ids.p, ns, smn, sext, leaf_max, ctx->nodes.p, root_slot, pair_base, ctx->bvh_prim_id.p, nb,
+                  ctx->stream, &info));
+    const uint32_t total_depth = nb ? 1 + std::max(big.depth, info.depth) : info.depth;
+    if (total_depth > 64) return 0;
+    CK(gather_prims(ctx->prims_flat.p, ctx->bvh_prim_id.p, ctx->prims_bvh.p, n, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_nodes = info.n_nodes;
+    *depth = total_depth;
+    *built = true;
+    return 0;
+}
+
+
 int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     if (!ctx) return fail(nullptr, 1, "ctx is null");
     const auto t_begin = std::chrono::steady_clock::now();
@@ -350,23 +512,22 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     // Instanced spheres (Translate / RotateY around a sphere): a rigid transform keeps a sphere a sphere, so they
     // are lowered to world-space spheres; the chain is kept only for the texture coordinates (getSphereUv works on
     // the object-space normal, hittable.zig:127).  `wprims` = the prims with such centres moved to world space.
-    std::vector<rtw_prim> wprims(s->prims, s->prims + n);
-    for (uint32_t i = 0; i < n; ++i) {
-        rtw_prim &p = wprims[i];
-        if (p.xform < 0 || (p.kind != RTW_PRIM_SPHERE && p.kind != RTW_PRIM_MOVING_SPHERE)) continue;
-        const XformD x = compose_chain_d(s, p.xform);
-        x.to_world(&s->prims[i].v[0], &p.v[0]);
-        if (p.kind == RTW_PRIM_MOVING_SPHERE) x.to_world(&s->prims[i].v[3], &p.v[3]);
-    }
-    // reference point for big spheres: centroid of the centres of everything that is not big
-    double cen[3] = {0, 0, 0};
-    uint32_t ncen = 0;
+    Laps laps;
+    std::vector<rtw_prim> wprims(n);
     std::vector<Box3d> boxes(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        {
-            const rtw_prim &wp = wprims[i];
-            if (wp.xform >= 0 && (wp.kind == RTW_PRIM_SPHERE || wp.kind == RTW_PRIM_MOVING_SPHERE)) {
-                rtw_prim q = wp;
+    // reference point for big spheres: centroid of the centres of everything that is not big (summed per fixed
+    // chunk, chunks in order: the same bits on every machine)
+    std::vector<std::array<double, 4>> cen_part(n_chunks_of(n), std::array<double, 4>{0, 0, 0, 0});
+    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+        std::array<double, 4> acc{0, 0, 0, 0};
+        for (uint32_t i = lo; i < hi; ++i) {
+            rtw_prim &p = wprims[i];
+            p = s->prims[i];
+            if (p.xform >= 0 && (p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE)) {
+                const XformD x = compose_chain_d(s, p.xform);
+                x.to_world(&s->prims[i].v[0], &p.v[0]);
+                if (p.kind == RTW_PRIM_MOVING_SPHERE) x.to_world(&s->prims[i].v[3], &p.v[3]);
+                rtw_prim q = p;
                 q.xform = -1;  // already in world space: exact box instead of the box of a rotated box ...
                 boxes[i] = leaf_box(s, q);
                 // ... padded: the reference-order fp32 probe intersects in OBJECT space, so its hit points carry the
@@ -377,13 +538,16 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             } else {
                 boxes[i] = leaf_box(s, s->prims[i]);
             }
+            if (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius) continue;
+            for (int a = 0; a < 3; ++a) acc[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
+            acc[3] += 1.0;
         }
-        const rtw_prim &p = wprims[i];
-        if (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius) continue;
-        for (int a = 0; a < 3; ++a) cen[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
-        ++ncen;
-    }
-    if (ncen) for (double &c : cen) c /= ncen;
+        cen_part[chunk] = acc;
+    });
+    double cen[3] = {0, 0, 0}, ncen = 0;
+    for (const auto &part : cen_part) { cen[0] += part[0]; cen[1] += part[1]; cen[2] += part[2]; ncen += part[3]; }
+    if (ncen > 0) for (double &c : cen) c /= ncen;
+    laps.lap("copy + leaf boxes");
 
     // ---- lower to fp32 records --------------------------------------------------------------------
     std::vector<DevPrim> flat(n);
@@ -391,8 +555,6 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     std::vector<DevBigSphere> bigs;
     std::vector<DevXform> xforms;
     std::map<int, int> xform_slot;
-    std::vector<RawPrim> raw(n);
-    std::vector<RawXform> chains;
     auto xform_slot_of = [&](int x) {
         auto it = xform_slot.find(x);
         if (it == xform_slot.end()) {
@@ -401,7 +563,9 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         }
         return it->second;
     };
-    for (uint32_t i = 0; i < n; ++i) {
+    // Plain primitives (no instance chain, not a big sphere) touch no shared table and are lowered in parallel; the
+    // rest follow in index order, which fixes the numbering of `bigs` and of the transform slots.
+    auto lower = [&](uint32_t i) -> bool {
         const rtw_prim &p = wprims[i];
         DevPrim d{};
         prim_mat[i] = p.material;
@@ -409,7 +573,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         uint32_t sphere_xf = 0;  // xform slot + 1 of an instanced sphere (uv only)
         if (p.xform >= 0 && (p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE)) {
             sphere_xf = (uint32_t)xform_slot_of(p.xform) + 1u;
-            if (sphere_xf > 0xFFFu) return fail(ctx, 1, "too many distinct instance chains on spheres (max 4095)");
+            if (sphere_xf > 0xFFFu) return false;
         }
         if (p.kind == RTW_PRIM_SPHERE) {
             d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
@@ -456,29 +620,50 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         d.b.w = bits_to_float(meta | (sphere_xf << 20));
         flat[i] = d;
 
-        RawPrim &r = raw[i];  // the probe keeps the reference's object-space fields + nested chain
-        r.kind = p.kind; r.material = p.material;
-        std::memcpy(r.v, s->prims[i].v, sizeof r.v);
-        r.chain_begin = (uint32_t)chains.size();
-        std::vector<RawXform> tmp;
-        for (int x = p.xform; x >= 0; x = s->xforms[x].outer) {
-            RawXform rx{};
-            rx.kind = s->xforms[x].kind;
-            rx.v[0] = s->xforms[x].v[0]; rx.v[1] = s->xforms[x].v[1]; rx.v[2] = s->xforms[x].v[2];
-            tmp.push_back(rx);
+        return true;
+    };
+    std::vector<std::vector<uint32_t>> special(n_chunks_of(n));
+    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            const rtw_prim &p = wprims[i];
+            if (p.xform >= 0 || (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius)) special[chunk].push_back(i);
+            else lower(i);
         }
-        std::reverse(tmp.begin(), tmp.end());  // outermost first
-        r.chain_len = (uint32_t)tmp.size();
-        chains.insert(chains.end(), tmp.begin(), tmp.end());
-    }
+    });
+    for (const auto &part : special)
+        for (uint32_t i : part)
+            if (!lower(i)) return fail(ctx, 1, "too many distinct instance chains on spheres (max 4095)");
+    laps.lap("lower to fp32");
 
     // ---- BVH ------------------------------------------------------------------------------------------
+    // Small and medium scenes: binned SAH on the host (best trees, microseconds to milliseconds).  Large scenes:
+    // Morton/Karras build on the device (rtw_lbvh.cu), with the few primitives that dwarf the rest (the ground
+    // sphere) kept out of the Morton order and grafted next to the root as their own host-built subtree.
     uint32_t leaf_max = 4;
     if (const char *e = getenv("RTW_BVH_LEAF_MAX")) leaf_max = (uint32_t)std::max(1, std::min(15, atoi(e)));  // 4-bit count in node refs
-    BvhResult bvh = build_bvh(boxes, leaf_max);
-    if (bvh.depth > (uint32_t)64) return fail(ctx, 2, "BVH depth %u exceeds the traversal stack", bvh.depth);
-    std::vector<DevPrim> leaf_order(n);
-    for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
+    CK(ctx->prims_flat.upload(flat));
+    const auto t_bvh = std::chrono::steady_clock::now();
+    bool use_lbvh = n >= kLbvhAutoMin;
+    if (const char *e = getenv("RTW_BVH_BUILDER")) use_lbvh = std::strcmp(e, "lbvh") == 0 && n >= 64;
+    uint32_t bvh_n_nodes = 0, bvh_depth = 0;
+    bool bvh_root_is_leaf = false, bvh_on_device = false;
+    if (use_lbvh) {
+        // not suitable (too deep for the traversal stack / degenerate input): the host builder below takes over
+        if (int rc = build_bvh_on_device(ctx, boxes, leaf_max, &bvh_n_nodes, &bvh_depth, &bvh_on_device)) return rc;
+    }
+    if (!bvh_on_device) {
+        BvhResult bvh = build_bvh(boxes, leaf_max);
+        if (bvh.depth > (uint32_t)64) return fail(ctx, 2, "BVH depth %u exceeds the traversal stack", bvh.depth);
+        std::vector<DevPrim> leaf_order(n);
+        for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
+        CK(ctx->prims_bvh.upload(leaf_order));
+        CK(ctx->bvh_prim_id.upload(bvh.order));
+        CK(ctx->nodes.upload(bvh.nodes));
+        bvh_n_nodes = (uint32_t)bvh.nodes.size(); bvh_depth = bvh.depth; bvh_root_is_leaf = bvh.root_is_leaf;
+    }
+    laps.lap("bvh");
+    ctx->stats.ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_bvh).count();
+    ctx->stats.bvh_builder = bvh_on_device ? RTW_BVH_BUILDER_LBVH : RTW_BVH_BUILDER_SAH;
 
     // ---- shared-memory image for the flat scan: segmented by kind, small spheres in groups of four --------
     FlatLayout fl{};
@@ -629,6 +814,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         fl.total_f4 = (uint32_t)blob.size();
     }
 
+    laps.lap("flat-scan image");
     // ---- materials / textures -------------------------------------------------------------------------
     std::vector<DevMaterial> mats(s->n_materials);
     for (uint32_t i = 0; i < s->n_materials; ++i) {
@@ -673,33 +859,38 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     }
 
     CK(ctx->flat_blob.upload(blob));
-    CK(ctx->prims_flat.upload(flat));
-    CK(ctx->prims_bvh.upload(leaf_order));
-    CK(ctx->bvh_prim_id.upload(bvh.order));
     CK(ctx->prim_material.upload(prim_mat));
-    CK(ctx->nodes.upload(bvh.nodes));
     CK(ctx->xforms.upload(xforms));
     CK(ctx->bigs.upload(bigs));
     CK(ctx->materials.upload(mats));
     CK(ctx->textures.upload(texs));
     CK(ctx->images.upload(imgs));
     CK(ctx->perlins.upload(perl));
-    CK(ctx->raw_prims.upload(raw));
-    CK(ctx->raw_chains.upload(chains));
+    ctx->raw_prims.release(); ctx->raw_chains.release();  // reference-order probe tables: built on first use
+    ctx->raw = RawScene{};
+    ctx->host_inst_orig.clear();
+    for (uint32_t i = 0; i < n; ++i)
+        if (wprims[i].xform >= 0 && (wprims[i].kind == RTW_PRIM_SPHERE || wprims[i].kind == RTW_PRIM_MOVING_SPHERE)) {
+            std::array<double, 10> v;
+            std::memcpy(v.data(), s->prims[i].v, sizeof(double) * 10);
+            ctx->host_inst_orig.emplace_back(i, v);
+        }
+    ctx->host_prims = std::move(wprims);
+    ctx->host_xforms.assign(s->xforms, s->xforms + s->n_xforms);
+    laps.lap("tables + upload");
 
     DevScene &d = ctx->scene;
     d.flat_blob = ctx->flat_blob.p; d.flat = fl;
     d.prims_flat = ctx->prims_flat.p; d.prims_bvh = ctx->prims_bvh.p; d.bvh_prim_id = ctx->bvh_prim_id.p;
     d.prim_material = ctx->prim_material.p; d.nodes = ctx->nodes.p; d.xforms = ctx->xforms.p; d.bigs = ctx->bigs.p;
     d.materials = ctx->materials.p; d.textures = ctx->textures.p; d.images = ctx->images.p; d.perlins = ctx->perlins.p;
-    d.n_prims = n; d.n_nodes = (uint32_t)bvh.nodes.size(); d.n_xforms = (uint32_t)xforms.size();
+    d.n_prims = n; d.n_nodes = bvh_n_nodes; d.n_xforms = (uint32_t)xforms.size();
     d.n_materials = s->n_materials; d.n_textures = s->n_textures;
-    d.root_is_leaf = bvh.root_is_leaf ? 1u : 0u;
-    ctx->raw = RawScene{ctx->raw_prims.p, ctx->raw_chains.p, ctx->nodes.p, ctx->bvh_prim_id.p, n, d.root_is_leaf};
+    d.root_is_leaf = bvh_root_is_leaf ? 1u : 0u;
     ctx->n_prims = n;
-    ctx->root_is_leaf = bvh.root_is_leaf;
-    ctx->stats.bvh_nodes = (uint32_t)bvh.nodes.size();
-    ctx->stats.bvh_depth = bvh.depth;
+    ctx->root_is_leaf = bvh_root_is_leaf;
+    ctx->stats.bvh_nodes = bvh_n_nodes;
+    ctx->stats.bvh_depth = bvh_depth;
     CK(cudaDeviceSynchronize());
     ctx->stats.ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     ctx->have_scene = true;
@@ -877,12 +1068,12 @@ int rtw_cuda_render(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params
     ctx->stats.n_launches += 1;
     if (int rc = fetch_counters(ctx)) return rc;
     if (!(p->flags & RTW_FLAG_COUNT_EVENTS)) {
-        const uint64_t nan = ctx->stats.nan_pixels;
-        const double mu = ctx->stats.ms_upload, mt = ctx->stats.ms_trace, mr = ctx->stats.ms_resolve;
-        const uint32_t nl = ctx->stats.n_launches, vu = ctx->stats.variant_used, bn = ctx->stats.bvh_nodes, bd = ctx->stats.bvh_depth;
+        const rtw_stats keep = ctx->stats;  // no event counters in this mode: keep timings and scene facts only
         ctx->stats = rtw_stats{};
-        ctx->stats.nan_pixels = nan; ctx->stats.ms_upload = mu; ctx->stats.ms_trace = mt; ctx->stats.ms_resolve = mr;
-        ctx->stats.n_launches = nl; ctx->stats.variant_used = vu; ctx->stats.bvh_nodes = bn; ctx->stats.bvh_depth = bd;
+        ctx->stats.nan_pixels = keep.nan_pixels; ctx->stats.ms_upload = keep.ms_upload; ctx->stats.ms_trace = keep.ms_trace;
+        ctx->stats.ms_resolve = keep.ms_resolve; ctx->stats.n_launches = keep.n_launches; ctx->stats.variant_used = keep.variant_used;
+        ctx->stats.bvh_nodes = keep.bvh_nodes; ctx->stats.bvh_depth = keep.bvh_depth;
+        ctx->stats.ms_bvh_build = keep.ms_bvh_build; ctx->stats.bvh_builder = keep.bvh_builder;
         ctx->stats.paths = (uint64_t)npx * spp;
     }
     return 0;
@@ -947,6 +1138,40 @@ int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera
     return 0;
 }
 
+// Tables of the reference-order probe (the reference's own object-space f64 fields and nested Translate/RotateY
+// chains, hittable.zig:472-596): test infrastructure of the parity suite, so built and uploaded on first use only.
+static int ensure_raw_scene(rtw_ctx *ctx) {
+    if (ctx->raw.prims) return 0;
+    const uint32_t n = ctx->n_prims;
+    std::vector<RawPrim> raw(n);
+    std::vector<RawXform> chains;
+    for (uint32_t i = 0; i < n; ++i) {
+        const rtw_prim &p = ctx->host_prims[i];
+        RawPrim &r = raw[i];
+        r.kind = p.kind; r.material = p.material;
+        std::memcpy(r.v, p.v, sizeof r.v);
+        r.chain_begin = (uint32_t)chains.size();
+        r.chain_len = 0;
+        if (p.xform < 0) continue;
+        std::vector<RawXform> tmp;
+        for (int x = p.xform; x >= 0; x = ctx->host_xforms[x].outer) {
+            RawXform rx{};
+            rx.kind = ctx->host_xforms[x].kind;
+            rx.v[0] = ctx->host_xforms[x].v[0]; rx.v[1] = ctx->host_xforms[x].v[1]; rx.v[2] = ctx->host_xforms[x].v[2];
+            tmp.push_back(rx);
+        }
+        std::reverse(tmp.begin(), tmp.end());  // outermost first
+        r.chain_len = (uint32_t)tmp.size();
+        chains.insert(chains.end(), tmp.begin(), tmp.end());
+    }
+    for (const auto &orig : ctx->host_inst_orig) std::memcpy(raw[orig.first].v, orig.second.data(), sizeof raw[orig.first].v);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->raw_prims.upload(raw));
+    CK(ctx->raw_chains.upload(chains));
+    ctx->raw = RawScene{ctx->raw_prims.p, ctx->raw_chains.p, ctx->nodes.p, ctx->bvh_prim_id.p, n, ctx->scene.root_is_leaf};
+    return 0;
+}
+
 static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_camera *cam, uint32_t width, uint32_t height,
                       uint32_t precision, uint32_t variant_req, uint32_t *prim_id, double *t, double *normal, double *uv) {
     if (!ctx) return fail(nullptr, 1, "ctx is null");
@@ -998,6 +1223,7 @@ static int probe_impl(rtw_ctx *ctx, uint32_t n, const double *rays, const rtw_ca
         if (normal) for (size_t k = 0; k < (size_t)n * 3; ++k) normal[k] = hn[k];
         if (uv) for (size_t k = 0; k < (size_t)n * 2; ++k) uv[k] = hu[k];
     } else {
+        if ((rc = ensure_raw_scene(ctx))) { cleanup(); return rc; }
         RawCamera rc_cam{};
         if (!rays) {
             for (int a = 0; a < 3; ++a) {

@@ -46,6 +46,10 @@ void write_node(BvhNode &n, const Aabb &b, uint32_t a, uint32_t cnt) {
 
 }  // namespace
 
+void box_to_f32(const Box3d &b, float out[6]) {
+    for (int a = 0; a < 3; ++a) { out[a] = down(b.mn[a]); out[3 + a] = up(b.mx[a]); }
+}
+
 BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
     BvhResult out;
     const uint32_t n = (uint32_t)boxes.size();

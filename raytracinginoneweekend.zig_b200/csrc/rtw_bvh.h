@@ -24,4 +24,7 @@ struct BvhResult {
 // `max_leaf` primitives.  Node boxes are fp32, rounded outward from the f64 boxes.
 BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf = 4);
 
+// The f64 box rounded outward to fp32: out = (min xyz, max xyz).
+void box_to_f32(const Box3d &b, float out[6]);
+
 }  // namespace rtw

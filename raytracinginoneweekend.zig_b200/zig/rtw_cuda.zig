@@ -3,7 +3,7 @@
 //! Field order and types mirror the header one for one; tests/test_abi.py pins the C side.
 const std = @import("std");
 
-pub const ABI_VERSION: u32 = 1;
+pub const ABI_VERSION: u32 = 2;
 pub const MISS: u32 = 0xFFFFFFFF;
 
 pub const PrimKind = enum(u32) { sphere = 0, moving_sphere = 1, xy_rect = 2, xz_rect = 3, yz_rect = 4 };

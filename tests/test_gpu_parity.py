@@ -102,8 +102,11 @@ def test_trace_rays_random_scene(rtw, oracle, ctx, seed):
     assert (a[0] != oid).mean() <= 1e-3
 
 
-def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx):
-    """10^4-sphere field (config C4's generator at grid 50): device BVH == device linear scan == oracle."""
+@pytest.mark.parametrize("builder", ["sah", "lbvh"])
+def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx, monkeypatch, builder):
+    """10^4-sphere field (config C4's generator at grid 50): device BVH == device linear scan == oracle, for the
+    host (binned SAH) and the device (Morton / radix tree) builder."""
+    monkeypatch.setenv("RTW_BVH_BUILDER", builder)
     hs = rtw.HostScene(rtw.host_lib.SCENE_SPHERE_FIELD, grid=50)
     osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
     ctx.upload_scene(hs.desc, keep=hs)
@@ -118,7 +121,63 @@ def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx):
     bvh = ctx.trace_rays(rays, 32, rtw.abi.VARIANT_MEGA_BVH)
     assert np.array_equal(flat[0], bvh[0]) and np.array_equal(flat[1], bvh[1])
     assert np.array_equal(bvh[0], oid) and np.array_equal(bvh[1], ot)
-    assert ctx.stats()["bvh_depth"] <= 64
+    st = ctx.stats()
+    assert st["bvh_depth"] <= 64
+    assert st["bvh_builder"] == (rtw.abi.BVH_BUILDER_LBVH if builder == "lbvh" else rtw.abi.BVH_BUILDER_SAH)
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_device_built_bvh_mixed_scene(rtw, oracle, ctx, monkeypatch, seed):
+    """Device builder on a mixed scene (rects, instanced boxes, moving and instanced spheres, a ground sphere that
+    dwarfs the rest and is grafted next to the root): reference-order probe through the BVH == linear scan == oracle."""
+    monkeypatch.setenv("RTW_BVH_BUILDER", "lbvh")
+    rng = np.random.default_rng(seed)
+    desc = scene_util.random_scene(rng, n_spheres=400, n_moving=200, n_rects=60, n_boxes=8, n_inst_spheres=20)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    ctx.upload_scene(desc, keep=desc)
+    st = ctx.stats()
+    assert st["bvh_builder"] == rtw.abi.BVH_BUILDER_LBVH and 2 <= st["bvh_depth"] <= 64 and st["bvh_nodes"] >= 4
+    rays = scene_util.random_rays(rng, 40000)
+    for precision in (32, 64):
+        oid, ot, on, _ = osc.trace_rays(rays, precision)
+        gid, gt, gn, _ = ctx.trace_rays(rays, precision, rtw.abi.VARIANT_MEGA_BVH)
+        assert np.array_equal(gid, oid) and np.array_equal(gt, ot) and np.array_equal(gn, on)
+    a = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_FLAT)
+    b = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_BVH)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # the same paths whichever builder made the tree (the BVH only culls)
+    hs_cam = rtw.camera_init((26, 6, 8), (0, 0, 0), (0, 1, 0), 40.0, 1.5, 0.0, 10.0, 0.0, 1.0)
+    p = ctx.params(96, 64, 0, 8, 8, 20, rtw.abi.VARIANT_MEGA_BVH, rtw.abi.FLAG_DETERMINISTIC, 7, (0.7, 0.8, 1.0))
+    _, acc_l = ctx.render(hs_cam, p, want_accum=True)
+    monkeypatch.setenv("RTW_BVH_BUILDER", "sah")
+    ctx.upload_scene(desc, keep=desc)
+    assert ctx.stats()["bvh_builder"] == rtw.abi.BVH_BUILDER_SAH
+    _, acc_s = ctx.render(hs_cam, p, want_accum=True)
+    assert np.array_equal(acc_l, acc_s)
+
+
+def test_device_built_bvh_coincident_centroids(rtw, oracle, ctx, monkeypatch):
+    """Equal Morton keys (stacks of concentric spheres): the radix tree splits ties by position and stays shallow."""
+    monkeypatch.setenv("RTW_BVH_BUILDER", "lbvh")
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    for k in range(300):
+        b.sphere((-50, 0, 0), 0.5 + 0.001 * k, m)
+        b.sphere((50, 0, 0), 0.5 + 0.001 * (k % 7), m)
+    desc = b.build()
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    ctx.upload_scene(desc, keep=desc)
+    st = ctx.stats()
+    assert st["bvh_builder"] == rtw.abi.BVH_BUILDER_LBVH and st["bvh_depth"] <= 16
+    rng = np.random.default_rng(3)
+    n = 4000
+    rays = np.zeros((n, 7))
+    rays[:, 0:3] = rng.uniform(-60, 60, (n, 3)) * [1, 0.005, 0.005]
+    rays[:, 3:6] = rng.normal(size=(n, 3)) * [1, 0.002, 0.002]
+    oid, ot, _, _ = osc.trace_rays(rays, 32)
+    gid, gt, _, _ = ctx.trace_rays(rays, 32, rtw.abi.VARIANT_MEGA_BVH)
+    assert (oid != MISS).mean() > 0.3
+    assert np.array_equal(gid, oid) and np.array_equal(gt, ot)
 
 
 def test_ties_later_element_wins(rtw, oracle, ctx):
@@ -468,7 +527,8 @@ def test_million_sphere_scene(rtw, oracle, ctx):
     assert hs.desc.n_prims > 990000
     ctx.upload_scene(hs.desc, keep=hs)
     st = ctx.stats()
-    assert st["bvh_depth"] <= 64 and st["bvh_nodes"] > hs.desc.n_prims
+    assert st["bvh_depth"] <= 64 and st["bvh_nodes"] > hs.desc.n_prims // 4
+    assert st["bvh_builder"] == rtw.abi.BVH_BUILDER_LBVH and st["ms_bvh_build"] < st["ms_upload"]
     osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
     W, H = 160, 90
     cam = hs.camera(aspect=W / H)
