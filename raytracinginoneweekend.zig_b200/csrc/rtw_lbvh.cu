@@ -1,7 +1,7 @@
 // rtw_lbvh.cu — BVH construction on the device: 63-bit Morton codes of the leaf-box centroids, one
 // radix sort, Karras' parallel binary radix tree, a bottom-up box fit, and an emit pass that folds
 // every subtree of <= max_leaf primitives into one leaf and writes the traversal's node layout
-// (rtw_device.cuh) directly.  Leaf boxes are the ones the reference's `boudingBox` methods define
+// (rtw_device.cuh) directly, in pre-order.  Leaf boxes are the ones the reference's `boudingBox` methods define
 // (src/rtw/hittable.zig:133-143,203-217,305-316,358-369,411-422,491-498,598-603), computed by the caller.
 #include "rtw_lbvh.h"
 
@@ -90,10 +90,12 @@ __device__ __forceinline__ Box prim_box(const float *__restrict__ boxes, uint32_
     return Box{b[0], b[1], b[2], b[3], b[4], b[5]};
 }
 
-// ibox[2i] = (min, bits(levels)), ibox[2i+1] = (max, -); written once by the second thread to reach node i
-__device__ __forceinline__ Box int_box(const float4 *ibox, uint32_t i, uint32_t &levels) {
+// ibox[2i] = (min, bits(levels)), ibox[2i+1] = (max, bits(pairs)); written once by the second thread to reach node i.
+// levels = height of the emitted subtree (a leaf = 1), pairs = sibling pairs it emits (0 when folded into a leaf).
+__device__ __forceinline__ Box int_box(const float4 *ibox, uint32_t i, uint32_t &levels, uint32_t &pairs) {
     const float4 a = __ldcg(ibox + 2 * (size_t)i), b = __ldcg(ibox + 2 * (size_t)i + 1);
     levels = __float_as_uint(a.w);
+    pairs = __float_as_uint(b.w);
     return Box{a.x, a.y, a.z, b.x, b.y, b.z};
 }
 
@@ -109,15 +111,35 @@ __global__ void k_fit(const float *__restrict__ boxes, const uint32_t *__restric
         __threadfence();
         const uint2 rg = range[cur];
         const uint32_t g = gamma[cur];
-        uint32_t ll = 1, lr = 1;
-        const Box L = rg.x == g ? prim_box(boxes, vals[g]) : int_box(ibox, g, ll);
-        const Box R = rg.y == g + 1 ? prim_box(boxes, vals[g + 1]) : int_box(ibox, g + 1, lr);
-        const uint32_t levels = (rg.y - rg.x + 1) <= max_leaf ? 1u : 1u + max(ll, lr);
+        uint32_t ll = 1, lr = 1, pl = 0, pr = 0;
+        const Box L = rg.x == g ? prim_box(boxes, vals[g]) : int_box(ibox, g, ll, pl);
+        const Box R = rg.y == g + 1 ? prim_box(boxes, vals[g + 1]) : int_box(ibox, g + 1, lr, pr);
+        const bool folded = (rg.y - rg.x + 1) <= max_leaf;
+        const uint32_t levels = folded ? 1u : 1u + max(ll, lr), pairs = folded ? 0u : 1u + pl + pr;
         ibox[2 * (size_t)cur] = make_float4(fminf(L.mnx, R.mnx), fminf(L.mny, R.mny), fminf(L.mnz, R.mnz), __uint_as_float(levels));
-        ibox[2 * (size_t)cur + 1] = make_float4(fmaxf(L.mxx, R.mxx), fmaxf(L.mxy, R.mxy), fmaxf(L.mxz, R.mxz), 0.f);
+        ibox[2 * (size_t)cur + 1] = make_float4(fmaxf(L.mxx, R.mxx), fmaxf(L.mxy, R.mxy), fmaxf(L.mxz, R.mxz), __uint_as_float(pairs));
         __threadfence();
         cur = parent_int[cur];
     }
+}
+
+// Pre-order position (in pairs) of the pair each surviving node emits: the left subtree directly behind its parent, the
+// right subtree behind the left one -- the layout the host builder produces, so a descent to the left stays in the
+// same or the next cache line.  Each node sums its own path to the root (depth <= ~64 steps).
+__global__ void k_offsets(uint32_t ns, const uint2 *__restrict__ range, const uint32_t *__restrict__ gamma,
+                          const uint32_t *__restrict__ parent_int, const uint32_t *__restrict__ survive,
+                          const float4 *__restrict__ ibox, uint32_t *__restrict__ pair_index) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns - 1 || !survive[i]) return;
+    uint32_t off = 0, c = i;
+    while (c != 0u) {
+        const uint32_t p = parent_int[c];
+        const uint32_t g = gamma[p];
+        off += 1u;
+        if (c == g + 1u && range[p].x != g) off += __float_as_uint(ibox[2 * (size_t)g + 1].w);  // pairs of the left sibling
+        c = p;
+    }
+    pair_index[i] = off;
 }
 
 __device__ __forceinline__ void store_node(BvhNode *nodes, uint32_t at, const Box &b, uint32_t a, uint32_t cnt) {
@@ -137,10 +159,8 @@ __global__ void k_emit(const float *__restrict__ boxes, const uint32_t *__restri
     const uint2 rg = range[i];
     const uint32_t g = gamma[i];
     const uint32_t at = pair_base + 2u * pair_index[i];
-    if (i == 0) {
-        uint32_t lv;
-        store_node(nodes, root_slot, int_box(ibox, 0, lv), at, 0u);
-    }
+    uint32_t lv, np;
+    if (i == 0) store_node(nodes, root_slot, int_box(ibox, 0, lv, np), at, 0u);
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
         const uint32_t c = g + side;
@@ -151,8 +171,7 @@ __global__ void k_emit(const float *__restrict__ boxes, const uint32_t *__restri
             store_node(nodes, at + side, prim_box(boxes, id), slot_base + c, 1u);
             continue;
         }
-        uint32_t lv;
-        const Box b = int_box(ibox, c, lv);
+        const Box b = int_box(ibox, c, lv, np);
         if (survive[c]) {
             store_node(nodes, at + side, b, pair_base + 2u * pair_index[c], 0u);
             continue;
@@ -196,11 +215,9 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
                        uint32_t slot_base, cudaStream_t st, LbvhInfo *info) {
     if (ns < 2 || ns <= max_leaf || max_leaf < 1 || max_leaf > 15 || (pair_base & 1u)) return cudaErrorInvalidValue;
     cudaError_t e;
-    size_t sort_bytes = 0, scan_bytes = 0;
+    size_t sort_bytes = 0;
     e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
                                         (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ns, 0, 63, st);
-    if (e != cudaSuccess) return e;
-    e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)(ns - 1), st);
     if (e != cudaSuccess) return e;
 
     // one arena, carved into the work arrays
@@ -210,7 +227,7 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     const size_t o_keys0 = take(8 * n), o_keys1 = take(8 * n), o_vals0 = take(4 * n), o_vals1 = take(4 * n);
     const size_t o_range = take(8 * n), o_gamma = take(4 * n), o_pint = take(4 * n), o_pleaf = take(4 * n);
     const size_t o_surv = take(4 * n), o_pair = take(4 * n), o_arr = take(4 * n), o_ibox = take(32 * n);
-    const size_t o_tmp = take(std::max(sort_bytes, scan_bytes));
+    const size_t o_tmp = take(sort_bytes);
     char *arena = nullptr;
     e = cudaMalloc(&arena, off);
     if (e != cudaSuccess) return e;
@@ -230,7 +247,7 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     const float widest = fmaxf(cext[0], fmaxf(cext[1], cext[2]));
     g.sx = g.sy = g.sz = widest > 0.f ? 2097152.0f / widest : 0.f;
     const uint32_t tpb = 256, blocks = (ns + tpb - 1) / tpb;
-    uint32_t tail[2] = {0, 0}, levels = 0;
+    uint32_t root_info[2] = {0, 0};  // levels, pairs
     auto done = [&](cudaError_t err) { cudaFree(arena); return err; };
 
     k_morton<<<blocks, tpb, 0, st>>>(d_boxes, d_ids, ns, g, keys0, vals0);
@@ -242,17 +259,16 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     if ((e = cudaMemsetAsync(arrivals, 0, 4 * n, st)) != cudaSuccess) return done(e);
     k_fit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, max_leaf, range, gamma, pint, pleaf, arrivals, ibox);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
-    tb = scan_bytes;
-    if ((e = cub::DeviceScan::ExclusiveSum(tmp, tb, surv, pair, (int)(ns - 1), st)) != cudaSuccess) return done(e);
+    k_offsets<<<blocks, tpb, 0, st>>>(ns, range, gamma, pint, surv, ibox, pair);
+    if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
     k_emit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, range, gamma, surv, pair, ibox, d_nodes, root_slot, pair_base, d_order, slot_base);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
-    if ((e = cudaMemcpyAsync(&tail[0], surv + (ns - 2), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
-    if ((e = cudaMemcpyAsync(&tail[1], pair + (ns - 2), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
-    if ((e = cudaMemcpyAsync(&levels, reinterpret_cast<const char *>(ibox) + 12, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
+    if ((e = cudaMemcpyAsync(&root_info[0], reinterpret_cast<const char *>(ibox) + 12, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
+    if ((e = cudaMemcpyAsync(&root_info[1], reinterpret_cast<const char *>(ibox) + 28, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(e);
     if (info) {
-        info->n_nodes = pair_base + 2u * (tail[0] + tail[1]);
-        info->depth = levels;
+        info->n_nodes = pair_base + 2u * root_info[1];
+        info->depth = root_info[0];
     }
     return done(cudaSuccess);
 }
