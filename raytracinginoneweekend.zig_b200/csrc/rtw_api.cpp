@@ -40,32 +40,35 @@ thread_local std::string g_create_error;
 
 float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
+// Device array that only ever grows: a re-upload of a scene of the same or a smaller size reuses the allocation
+// (cudaMalloc / cudaFree of 100 MB-class buffers were measured to stall for hundreds of milliseconds now and then).
 template <class T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
-    cudaError_t upload(const std::vector<T> &h) {
-        release();
-        n = h.size();
-        if (n == 0) {  // keep a valid pointer so kernels never see null tables
-            return cudaMalloc(&p, sizeof(T));
-        }
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e != cudaSuccess) return e;
-        return cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
-    }
+    size_t n = 0;    // elements in use
+    size_t cap = 0;  // elements allocated
     cudaError_t alloc(size_t count) {
-        release();
+        const size_t want = std::max<size_t>(1, count);  // keep a valid pointer so kernels never see null tables
+        if (want > cap) {
+            release();
+            cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+            if (e != cudaSuccess) { p = nullptr; return e; }
+            cap = want;
+        }
         n = count;
-        return cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
+        return cudaSuccess;
+    }
+    cudaError_t upload(const std::vector<T> &h) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
     }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
-        n = 0;
+        n = cap = 0;
     }
 };
-
 
 // Splits [0, n) into fixed chunks (independent of the machine, so chunk-ordered reductions are reproducible) and runs
 // fn(chunk, lo, hi) over them on a few threads when the scene is large; small scenes stay on the calling thread.
@@ -124,6 +127,10 @@ struct rtw_ctx {
     DevBuf<DevPerlin> perlins;
     DevBuf<RawPrim> raw_prims;
     DevBuf<RawXform> raw_chains;
+    DevBuf<float> lbvh_boxes;      // device BVH build: fp32 leaf boxes, primitive ids, work arena (kept between uploads)
+    DevBuf<uint32_t> lbvh_ids;
+    DevBuf<unsigned char> lbvh_arena;
+    std::vector<Box3d> scratch_boxes;  // host scratch reused between uploads (first touch of 50-100 MB is not free)
     std::vector<cudaArray_t> image_arrays;
     std::vector<cudaTextureObject_t> image_tex;
     DevScene scene{};
@@ -376,6 +383,7 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
     ctx->prims_flat.release(); ctx->prims_bvh.release(); ctx->bvh_prim_id.release(); ctx->prim_material.release();
     ctx->nodes.release(); ctx->xforms.release(); ctx->bigs.release(); ctx->materials.release(); ctx->textures.release();
     ctx->images.release(); ctx->perlins.release(); ctx->raw_prims.release(); ctx->raw_chains.release();
+    ctx->lbvh_boxes.release(); ctx->lbvh_ids.release(); ctx->lbvh_arena.release();
     ctx->accum.release(); ctx->rgb8.release(); ctx->tile_counter.release(); ctx->stat_counters.release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -391,6 +399,7 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
 static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, uint32_t leaf_max, uint32_t *n_nodes,
                                uint32_t *depth, bool *built) {
     *built = false;
+    Laps laps;
     const uint32_t n = (uint32_t)boxes.size();
     std::vector<float> fb(6 * (size_t)n);
     struct Part {
@@ -453,6 +462,7 @@ static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, ui
     const uint32_t nb = (uint32_t)big_ids.size(), ns = (uint32_t)small_ids.size();
     if (ns < 2 || ns <= leaf_max) return 0;
     const float *all_mn = all.bmn, *all_mx = all.bmx, *smn = rest.cmn, *smx = rest.cmx;
+    laps.lap("  lbvh host prep");
     const float sext[3] = {smx[0] - smn[0], smx[1] - smn[1], smx[2] - smn[2]};
 
     BvhResult big;
@@ -476,24 +486,27 @@ static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, ui
         head.assign(2, BvhNode{0, 0, 0, 0, 0, 0, 0, 0});
     }
     CK(cudaSetDevice(ctx->device));
-    DevBuf<float> d_boxes;
-    DevBuf<uint32_t> d_ids;
-    struct Scope { DevBuf<float> &a; DevBuf<uint32_t> &b; ~Scope() { a.release(); b.release(); } } scope{d_boxes, d_ids};
+    DevBuf<float> &d_boxes = ctx->lbvh_boxes;
+    DevBuf<uint32_t> &d_ids = ctx->lbvh_ids;
     CK(d_boxes.upload(fb));
     CK(d_ids.upload(small_ids));
+    CK(ctx->lbvh_arena.alloc(lbvh_arena_bytes(ns)));
     CK(ctx->nodes.alloc((size_t)pair_base + 2 * (size_t)(ns - 1)));
     CK(ctx->bvh_prim_id.alloc(n));
     CK(ctx->prims_bvh.alloc(n));
     CK(cudaMemcpy(ctx->nodes.p, head.data(), head.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
     if (nb) CK(cudaMemcpy(ctx->bvh_prim_id.p, big_order.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
     CK(cudaDeviceSynchronize());
+    laps.lap("  lbvh alloc + H2D");
     LbvhInfo info;
     CK(build_lbvh(d_boxes.p, d_ids.p, ns, smn, sext, leaf_max, ctx->nodes.p, root_slot, pair_base, ctx->bvh_prim_id.p, nb,
-                  ctx->stream, &info));
+                  ctx->lbvh_arena.p, ctx->lbvh_arena.cap, ctx->stream, &info));
+    laps.lap("  lbvh device build");
     const uint32_t total_depth = nb ? 1 + std::max(big.depth, info.depth) : info.depth;
     if (total_depth > 64) return 0;
     CK(gather_prims(ctx->prims_flat.p, ctx->bvh_prim_id.p, ctx->prims_bvh.p, n, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    laps.lap("  lbvh gather");
     *n_nodes = info.n_nodes;
     *depth = total_depth;
     *built = true;
@@ -513,8 +526,10 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     // are lowered to world-space spheres; the chain is kept only for the texture coordinates (getSphereUv works on
     // the object-space normal, hittable.zig:127).  `wprims` = the prims with such centres moved to world space.
     Laps laps;
-    std::vector<rtw_prim> wprims(n);
-    std::vector<Box3d> boxes(n);
+    std::vector<rtw_prim> wprims = std::move(ctx->host_prims);  // storage of the previous scene's copy, if any
+    wprims.resize(n);
+    std::vector<Box3d> &boxes = ctx->scratch_boxes;
+    boxes.resize(n);
     // reference point for big spheres: centroid of the centres of everything that is not big (summed per fixed
     // chunk, chunks in order: the same bits on every machine)
     std::vector<std::array<double, 4>> cen_part(n_chunks_of(n), std::array<double, 4>{0, 0, 0, 0});

@@ -6,6 +6,7 @@
 #include "rtw_lbvh.h"
 
 #include <algorithm>
+#include <cstdint>
 
 #include <cub/cub.cuh>
 
@@ -210,35 +211,51 @@ cudaError_t gather_prims(const DevPrim *src, const uint32_t *d_order, DevPrim *d
     return cudaGetLastError();
 }
 
-cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns, const float cmin[3], const float cext[3],
-                       uint32_t max_leaf, BvhNode *d_nodes, uint32_t root_slot, uint32_t pair_base, uint32_t *d_order,
-                       uint32_t slot_base, cudaStream_t st, LbvhInfo *info) {
-    if (ns < 2 || ns <= max_leaf || max_leaf < 1 || max_leaf > 15 || (pair_base & 1u)) return cudaErrorInvalidValue;
-    cudaError_t e;
-    size_t sort_bytes = 0;
-    e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ns, 0, 63, st);
+namespace {
+struct ArenaLayout {
+    size_t keys0, keys1, vals0, vals1, range, gamma, pint, pleaf, surv, pair, arrivals, ibox, tmp, total, sort_bytes;
+};
+cudaError_t arena_layout(uint32_t ns, ArenaLayout &a) {
+    a.sort_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, a.sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ns, 0, 63, 0);
     if (e != cudaSuccess) return e;
-
-    // one arena, carved into the work arrays
     const size_t n = ns;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes); return at; };
-    const size_t o_keys0 = take(8 * n), o_keys1 = take(8 * n), o_vals0 = take(4 * n), o_vals1 = take(4 * n);
-    const size_t o_range = take(8 * n), o_gamma = take(4 * n), o_pint = take(4 * n), o_pleaf = take(4 * n);
-    const size_t o_surv = take(4 * n), o_pair = take(4 * n), o_arr = take(4 * n), o_ibox = take(32 * n);
-    const size_t o_tmp = take(sort_bytes);
-    char *arena = nullptr;
-    e = cudaMalloc(&arena, off);
-    if (e != cudaSuccess) return e;
-    auto *keys0 = (uint64_t *)(arena + o_keys0), *keys1 = (uint64_t *)(arena + o_keys1);
-    auto *vals0 = (uint32_t *)(arena + o_vals0), *vals1 = (uint32_t *)(arena + o_vals1);
-    auto *range = (uint2 *)(arena + o_range);
-    auto *gamma = (uint32_t *)(arena + o_gamma), *pint = (uint32_t *)(arena + o_pint), *pleaf = (uint32_t *)(arena + o_pleaf);
-    auto *surv = (uint32_t *)(arena + o_surv), *pair = (uint32_t *)(arena + o_pair);
-    auto *arrivals = (unsigned int *)(arena + o_arr);
-    auto *ibox = (float4 *)(arena + o_ibox);
-    void *tmp = arena + o_tmp;
+    a.keys0 = take(8 * n); a.keys1 = take(8 * n); a.vals0 = take(4 * n); a.vals1 = take(4 * n);
+    a.range = take(8 * n); a.gamma = take(4 * n); a.pint = take(4 * n); a.pleaf = take(4 * n);
+    a.surv = take(4 * n); a.pair = take(4 * n); a.arrivals = take(4 * n); a.ibox = take(32 * n);
+    a.tmp = take(a.sort_bytes);
+    a.total = off;
+    return cudaSuccess;
+}
+}  // namespace
+
+size_t lbvh_arena_bytes(uint32_t ns) {
+    ArenaLayout a;
+    return arena_layout(ns, a) == cudaSuccess ? a.total : 0;
+}
+
+cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns, const float cmin[3], const float cext[3],
+                       uint32_t max_leaf, BvhNode *d_nodes, uint32_t root_slot, uint32_t pair_base, uint32_t *d_order,
+                       uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info) {
+    if (ns < 2 || ns <= max_leaf || max_leaf < 1 || max_leaf > 15 || (pair_base & 1u)) return cudaErrorInvalidValue;
+    cudaError_t e;
+    ArenaLayout L;
+    if ((e = arena_layout(ns, L)) != cudaSuccess) return e;
+    if (!d_arena || arena_bytes < L.total || (reinterpret_cast<uintptr_t>(d_arena) & 255u)) return cudaErrorInvalidValue;
+    const size_t n = ns;
+    char *arena = static_cast<char *>(d_arena);
+    auto *keys0 = (uint64_t *)(arena + L.keys0), *keys1 = (uint64_t *)(arena + L.keys1);
+    auto *vals0 = (uint32_t *)(arena + L.vals0), *vals1 = (uint32_t *)(arena + L.vals1);
+    auto *range = (uint2 *)(arena + L.range);
+    auto *gamma = (uint32_t *)(arena + L.gamma), *pint = (uint32_t *)(arena + L.pint), *pleaf = (uint32_t *)(arena + L.pleaf);
+    auto *surv = (uint32_t *)(arena + L.surv), *pair = (uint32_t *)(arena + L.pair);
+    auto *arrivals = (unsigned int *)(arena + L.arrivals);
+    auto *ibox = (float4 *)(arena + L.ibox);
+    void *tmp = arena + L.tmp;
+    const size_t sort_bytes = L.sort_bytes;
 
     Grid g;
     g.mnx = cmin[0]; g.mny = cmin[1]; g.mnz = cmin[2];
@@ -248,7 +265,7 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     g.sx = g.sy = g.sz = widest > 0.f ? 2097152.0f / widest : 0.f;
     const uint32_t tpb = 256, blocks = (ns + tpb - 1) / tpb;
     uint32_t root_info[2] = {0, 0};  // levels, pairs
-    auto done = [&](cudaError_t err) { cudaFree(arena); return err; };
+    auto done = [&](cudaError_t err) { return err; };
 
     k_morton<<<blocks, tpb, 0, st>>>(d_boxes, d_ids, ns, g, keys0, vals0);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);

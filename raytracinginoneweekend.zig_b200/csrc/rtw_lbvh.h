@@ -23,9 +23,11 @@ struct LbvhInfo {
 //   d_nodes   the subtree root goes to d_nodes[root_slot], child pairs from pair_base (even) on;
 //             capacity needed: pair_base + 2*(ns-1)
 //   d_order   leaf slot -> primitive id, written at [slot_base, slot_base + ns)
+//   d_arena   work memory of at least lbvh_arena_bytes(ns) bytes, 256-byte aligned (the caller keeps it between builds)
+size_t lbvh_arena_bytes(uint32_t ns);
 cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns, const float cmin[3], const float cext[3],
                        uint32_t max_leaf, BvhNode *d_nodes, uint32_t root_slot, uint32_t pair_base, uint32_t *d_order,
-                       uint32_t slot_base, cudaStream_t st, LbvhInfo *info);
+                       uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info);
 
 // dst[k] = src[order[k]] for k < n (primitives into leaf order)
 cudaError_t gather_prims(const DevPrim *src, const uint32_t *d_order, DevPrim *dst, uint32_t n, cudaStream_t st);

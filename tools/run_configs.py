@@ -65,7 +65,8 @@ for name, sid, grid, W, H, spp, variant, gate in CONFIGS:
     row = {"config": name, "prims": hs.desc.n_prims, "variant_used": st["variant_used"], "ms": ms, "mpaths_s": paths / ms / 1e3,
            "mrays_s": paths * rpp / ms / 1e3, "rays_per_path": rpp, "flops_per_ray": flops_ray,
            "fp32_frac": paths * rpp * flops_ray / (ms * 1e-3) / 1e12 / peak_tf, "peak_tflops": peak_tf,
-           "upload_ms": up["ms_upload"], "bvh_nodes": up["bvh_nodes"], "bvh_depth": up["bvh_depth"], "host_scene_s": t_host}
+           "upload_ms": up["ms_upload"], "bvh_build_ms": up["ms_bvh_build"],
+           "bvh_builder": "lbvh" if up["bvh_builder"] == abi.BVH_BUILDER_LBVH else "sah", "bvh_nodes": up["bvh_nodes"], "bvh_depth": up["bvh_depth"], "host_scene_s": t_host}
     if not args.no_cpu:
         osc = ob.OracleScene.from_desc(hs.desc, keep=hs)
         big = hs.desc.n_prims > 2000
