@@ -226,14 +226,20 @@ __device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, flo
 // `reach` = best.t * |d|: the bound is also skipped when even its nearest point lies beyond the current
 // closest hit (the big spheres — the ground — are tested first so that this culls)
 // b = (centre, R): the radius itself is stored (R^2 is one multiply away, R would be a MUFU)
-__device__ __forceinline__ bool bound_hit(const Ray &r, float inv_a, const float4 b, float reach) {
-    float ox, oy, oz, bp;
+// This is a CULLING test, so it uses the cheap form |oc|^2 a - (oc.d)^2 <= a R^2 (a = d.d) instead of the
+// cancellation-free perpendicular offset the member tests need, and pays for the fp32 cancellation with slack:
+// the left side carries an absolute error below 12 * 2^-24 * |oc|^2 a (three-term dot products, one FMA rounding),
+// so the bound is kept whenever lhs <= a (R^2 + 2e-6 |oc|^2).  False positives only cost time.
+__device__ __forceinline__ bool bound_hit(const Ray &r, float add, const float4 b, float reach) {
+    const float ox = r.ox - b.x, oy = r.oy - b.y, oz = r.oz - b.z;
     const float rr = b.w * b.w;
-    const float d = sphere_disc(r, inv_a, b.x, b.y, b.z, rr, ox, oy, oz, bp);
     const float oo = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+    const float bp = fmaf(ox, r.dx, fmaf(oy, r.dy, oz * r.dz));
+    const float lhs = fmaf(-bp, bp, oo * add);
+    const float rhs = fmaf(oo, 2e-6f, rr) * add;
     // origin outside the bound and either the bound is behind, or |oc| - R > reach, i.e. |oc|^2 > (reach + R)^2
     const float lim = fmaf(reach, fmaf(2.0f, b.w, reach), rr);
-    return d >= 0.0f && !(oo > rr && (bp > 0.0f || oo > lim));
+    return lhs <= rhs && !(oo > rr && (bp > 0.0f || oo > lim));
 }
 
 template <bool STATS>
@@ -315,7 +321,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
 #pragma unroll 1
         for (; gp < ge; gp += 5, ip += 4) {
             if (active) cn.add(ST_SPHERE_TESTS);  // the bound is a sphere test too
-            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0], best.t * len))) continue;
+            if (!__any_sync(0xffffffffu, active && bound_hit(r, add, gp[0], best.t * len))) continue;
             if (active) cn.add(ST_SPHERE_TESTS, 4);
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
             flat_static_pair<STATS>(r, add, inv_a, gp[1], gp[2], id.x, id.y, active, t_min, best, cn);
@@ -329,7 +335,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
 #pragma unroll 1
         for (; gp < ge; gp += 9, ip += 4) {
             if (active) cn.add(ST_SPHERE_TESTS);
-            if (!__any_sync(0xffffffffu, active && bound_hit(r, inv_a, gp[0], best.t * len))) continue;
+            if (!__any_sync(0xffffffffu, active && bound_hit(r, add, gp[0], best.t * len))) continue;
             if (active) { cn.add(ST_SPHERE_TESTS, 4); cn.add(ST_MOVING_TESTS, 4); }
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
 #pragma unroll
