@@ -239,7 +239,9 @@ __device__ __forceinline__ bool bound_hit(const Ray &r, float add, const float4 
     const float rhs = fmaf(oo, 2e-6f, rr) * add;
     // origin outside the bound and either the bound is behind, or |oc| - R > reach, i.e. |oc|^2 > (reach + R)^2
     const float lim = fmaf(reach, fmaf(2.0f, b.w, reach), rr);
-    return lhs <= rhs && !(oo > rr && (bp > 0.0f || oo > lim));
+    // bitwise, not short-circuit: the test stays one straight line of predicate logic (lim >= rr, so oo > lim implies
+    // the origin is outside)
+    return (lhs <= rhs) & !((oo > lim) | ((oo > rr) & (bp > 0.0f)));
 }
 
 template <bool STATS>
@@ -291,7 +293,9 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
     const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
     const float inv_a = rcp_approx(add);
     const float len = sqrt_approx(add) * 1.00001f;  // |d|, rounded up: best.t * len = reach of the current closest hit
-    FlatBest best{__int_as_float(0x7f800000), kMiss};
+    // inactive lanes scan with reach 0: a bound then passes only if their (stale) origin lies inside it, so they
+    // practically never keep a group alive in the votes below and the votes need no `active` term
+    FlatBest best{active ? __int_as_float(0x7f800000) : 0.0f, kMiss};
     const uint32_t *ids = reinterpret_cast<const uint32_t *>(s + L.off_ids);
 
     // ---- big static spheres: c term about the reference point ----
@@ -321,7 +325,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
 #pragma unroll 1
         for (; gp < ge; gp += 5, ip += 4) {
             if (active) cn.add(ST_SPHERE_TESTS);  // the bound is a sphere test too
-            if (!__any_sync(0xffffffffu, active && bound_hit(r, add, gp[0], best.t * len))) continue;
+            if (!__any_sync(0xffffffffu, bound_hit(r, add, gp[0], best.t * len))) continue;
             if (active) cn.add(ST_SPHERE_TESTS, 4);
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
             flat_static_pair<STATS>(r, add, inv_a, gp[1], gp[2], id.x, id.y, active, t_min, best, cn);
@@ -335,7 +339,7 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
 #pragma unroll 1
         for (; gp < ge; gp += 9, ip += 4) {
             if (active) cn.add(ST_SPHERE_TESTS);
-            if (!__any_sync(0xffffffffu, active && bound_hit(r, add, gp[0], best.t * len))) continue;
+            if (!__any_sync(0xffffffffu, bound_hit(r, add, gp[0], best.t * len))) continue;
             if (active) { cn.add(ST_SPHERE_TESTS, 4); cn.add(ST_MOVING_TESTS, 4); }
             const uint4 id = *reinterpret_cast<const uint4 *>(ip);
 #pragma unroll
