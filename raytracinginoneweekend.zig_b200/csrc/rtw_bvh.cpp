@@ -40,7 +40,7 @@ float up(double v) {
 }
 
 void write_node(BvhNode &n, const Aabb &b, uint32_t a, uint32_t cnt) {
-    n.mnx = b.mn[0]; n.mny = b.mn[1]; n.mnz = b.mn[2]; n.a = a;
+    n.mnx = b.mn[0]; n.mny = b.mn[1]; n.mnz = b.mn[2]; n.a = a | (cnt << kNodeRefShift);  // = the traversal's node reference
     n.mxx = b.mx[0]; n.mxy = b.mx[1]; n.mxz = b.mx[2]; n.b = cnt;
 }
 
@@ -241,7 +241,7 @@ BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
     out.root_is_leaf = out.nodes[0].b != 0;
     // keep reference order inside each leaf (ties then resolve like the linear scan without id lookups)
     for (const BvhNode &nd : out.nodes)
-        if (nd.b > 1) std::sort(out.order.begin() + nd.a, out.order.begin() + nd.a + nd.b);
+        if (nd.b > 1) std::sort(out.order.begin() + (nd.a & kNodeRefIndexMask), out.order.begin() + (nd.a & kNodeRefIndexMask) + nd.b);
     return out;
 }
 

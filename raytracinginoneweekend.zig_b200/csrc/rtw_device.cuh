@@ -29,10 +29,11 @@ struct __align__(16) DevPrim {
 
 struct __align__(16) BvhNode {
     float mnx, mny, mnz;
-    uint32_t a;  // interior: index of left child (right = a+1); leaf: first slot
+    uint32_t a;  // interior: index of left child (right = a+1); leaf: first slot | count << kNodeRefShift
     float mxx, mxy, mxz;
-    uint32_t b;  // interior: 0; leaf: primitive count (>0)
+    uint32_t b;  // interior: 0; leaf: primitive count (1..15)
 };
+constexpr uint32_t kNodeRefShift = 28, kNodeRefIndexMask = (1u << kNodeRefShift) - 1u;
 
 struct __align__(16) DevXform {
     // object = A*world + t with A = rotation about Y: x' = c*x - s*z, z' = s*x + c*z

@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
     uint32_t bounce = 0, cur_sample = 0, pixel = 0;
     bool alive = false, trav = false;
     BvhTraversal tv;
+    uint32_t stack[kBvhStack];
     tv.sp = 0; tv.cur = 0;
     for (;;) {
         const uint32_t idle = __ballot_sync(0xffffffffu, !trav);
@@ -278,13 +279,13 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
             const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
             const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
             if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
-                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS>(r, sc, 0.001f, cn);
+                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS>(r, sc, 0.001f, stack, cn);
             }
         }
         // ---- interior phase ----
 #pragma unroll 1
         for (uint32_t k = 0; k < rp.steps_per_round; ++k) {
-            if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, 0.001f, cn);
+            if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, 0.001f, stack, cn);
         }
     }
     if (STATS) cn.flush(rp.stats);

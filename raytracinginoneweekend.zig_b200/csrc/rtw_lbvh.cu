@@ -145,7 +145,7 @@ __global__ void k_offsets(uint32_t ns, const uint2 *__restrict__ range, const ui
 
 __device__ __forceinline__ void store_node(BvhNode *nodes, uint32_t at, const Box &b, uint32_t a, uint32_t cnt) {
     float4 *q = reinterpret_cast<float4 *>(nodes + at);
-    q[0] = make_float4(b.mnx, b.mny, b.mnz, __uint_as_float(a));
+    q[0] = make_float4(b.mnx, b.mny, b.mnz, __uint_as_float(a | (cnt << kNodeRefShift)));  // = the traversal's node reference
     q[1] = make_float4(b.mxx, b.mxy, b.mxz, __uint_as_float(cnt));
 }
 

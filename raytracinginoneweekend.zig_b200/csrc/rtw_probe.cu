@@ -180,7 +180,7 @@ __device__ bool ref_closest(const RawScene &sc, const RRay<R> &r, RRec<R> &best,
             }
         }
     };
-    if (sc.root_is_leaf) { leaf(sc.nodes[0].a, sc.nodes[0].b); return any; }
+    if (sc.root_is_leaf) { leaf(sc.nodes[0].a & kNodeRefIndexMask, sc.nodes[0].b); return any; }
     uint32_t stack[64];
     int sp = 0;
     stack[sp++] = sc.nodes[0].a;
@@ -189,7 +189,7 @@ __device__ bool ref_closest(const RawScene &sc, const RRay<R> &r, RRec<R> &best,
         for (int side = 0; side < 2; ++side) {
             const BvhNode n = sc.nodes[pair + side];
             if (!ref_slab<R>(n, r, t_min, closest)) continue;
-            if (n.b) leaf(n.a, n.b);
+            if (n.b) leaf(n.a & kNodeRefIndexMask, n.b);
             else if (sp < 64) stack[sp++] = n.a;
         }
     }

@@ -394,8 +394,8 @@ __device__ __forceinline__ bool slab(const BvhNode &n, const Ray &r, float idx, 
 
 constexpr int kBvhStack = 64;
 
-// stack entry / node reference: index in the low 28 bits, leaf primitive count in the top 4
-__device__ __forceinline__ uint32_t node_ref(uint32_t a, uint32_t b) { return a | (b << 28); }
+// stack entry / node reference: index in the low 28 bits, leaf primitive count in the top 4.  The builders store
+// BvhNode::a in exactly this form (kNodeRefShift), so a child reference is the loaded word itself.
 
 // Traversal state of one ray.  `step` performs at most one interior visit (both children of the
 // current node) followed by at most one leaf visit, so a warp can interleave traversal steps of its
@@ -404,9 +404,11 @@ struct BvhTraversal {
     float idx, idy, idz, add, inv_a;
     Hit h;
     uint32_t best_id;
-    uint32_t cur;  // node_ref of the node to visit next
+    uint32_t cur;  // reference of the node to visit next
     int sp;
-    uint32_t stack[kBvhStack];
+    // The stack itself is NOT a member: a dynamically indexed array inside the struct forces the whole struct into
+    // local memory (ncu r01_m: four LDL and three STL per interior visit); as a separate array only the pushes and
+    // pops touch local memory and the scalars above stay in registers.
 
     // returns true when the traversal is already finished (empty scene)
     __device__ __forceinline__ bool init(const Ray &r, const DevScene &sc) {
@@ -417,8 +419,7 @@ struct BvhTraversal {
         best_id = 0;
         sp = 0;
         if (sc.n_prims == 0) return true;
-        const BvhNode root = sc.nodes[0];
-        cur = node_ref(root.a, root.b);
+        cur = sc.nodes[0].a;
         return false;
     }
 
@@ -426,7 +427,8 @@ struct BvhTraversal {
 
     // one interior visit: both children of `cur` (precondition: !at_leaf()).  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
+                                                  Counters<STATS> &cn) {
         const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
         const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
         const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
@@ -435,7 +437,7 @@ struct BvhTraversal {
         float tl, tr;
         const bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
         const bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
-        const uint32_t el = node_ref(L.a, L.b), er = node_ref(R.a, R.b);
+        const uint32_t el = L.a, er = R.a;
         if (hl && hr) {
             const bool left_first = tl <= tr;
             stack[sp++] = left_first ? er : el;  // depth is bounded by the builder (<= kBvhStack)
@@ -451,7 +453,8 @@ struct BvhTraversal {
 
     // one leaf visit (precondition: at_leaf()): the only primitive-test site.  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
+                                              Counters<STATS> &cn) {
         const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint32_t slot = at + i;
@@ -471,9 +474,10 @@ struct BvhTraversal {
 
     // at most one interior visit followed by at most one leaf visit.  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
-        if (!at_leaf() && interior_step<STATS>(r, sc, t_min, cn)) return true;
-        if (at_leaf()) return leaf_step<STATS>(r, sc, t_min, cn);
+    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
+                                         Counters<STATS> &cn) {
+        if (!at_leaf() && interior_step<STATS>(r, sc, t_min, stack, cn)) return true;
+        if (at_leaf()) return leaf_step<STATS>(r, sc, t_min, stack, cn);
         return false;
     }
 };
@@ -481,8 +485,9 @@ struct BvhTraversal {
 template <bool STATS>
 __device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
     BvhTraversal tv;
+    uint32_t stack[kBvhStack];
     if (tv.init(r, sc)) return tv.h;
-    while (!tv.template step<STATS>(r, sc, t_min, cn)) {}
+    while (!tv.template step<STATS>(r, sc, t_min, stack, cn)) {}
     return tv.h;
 }
 

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_bvh(WfState st, const De
     uint32_t slot = 0;
     Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
     BvhTraversal tv;
+    uint32_t stack[kBvhStack];
     tv.sp = 0; tv.cur = 0;
     constexpr uint32_t kChunk = 32 * 8;
     for (;;) {
@@ -164,9 +165,9 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_bvh(WfState st, const De
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
         const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
         if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
-            if (trav && tv.at_leaf()) done = tv.template leaf_step<STATS>(r, sc, 0.001f, cn);
+            if (trav && tv.at_leaf()) done = tv.template leaf_step<STATS>(r, sc, 0.001f, stack, cn);
         }
-        if (trav && !done && !tv.at_leaf()) done = tv.template interior_step<STATS>(r, sc, 0.001f, cn);
+        if (trav && !done && !tv.at_leaf()) done = tv.template interior_step<STATS>(r, sc, 0.001f, stack, cn);
         if (done) {
             trav = false;
             st.rd[slot].w = tv.h.t;
