@@ -782,7 +782,8 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                 } else { mov.push_back(dummy); mov.push_back(zero4); ids.push_back(0); }
             }
         }
-        // rect runs: equal (xform slot, orientation), in order of first appearance
+        // rect runs: equal (xform slot, orientation); transforms in order of first appearance, the runs of one
+        // transform adjacent so the scan sets up the object-space ray once per instance
         std::vector<float4> runs;
         {
             std::vector<std::pair<int, uint32_t>> keys;  // (xform slot, kind)
@@ -796,16 +797,28 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                 if (k == keys.size()) { keys.push_back(key); members.emplace_back(); }
                 members[k].push_back(i);
             }
-            for (size_t k = 0; k < keys.size(); ++k) {
+            std::vector<size_t> order_k(keys.size());
+            for (size_t k = 0; k < keys.size(); ++k) order_k[k] = k;
+            auto first_with_slot = [&](int slot) { size_t k = 0; while (keys[k].first != slot) ++k; return k; };
+            std::stable_sort(order_k.begin(), order_k.end(), [&](size_t a, size_t b) {
+                return first_with_slot(keys[a].first) < first_with_slot(keys[b].first);
+            });
+            int prev_slot = 0;
+            bool have_prev = false;
+            for (size_t k : order_k) {
                 const uint32_t first = (uint32_t)(rect.size() / 2);
                 for (uint32_t i : members[k]) {
                     rect.push_back(flat[i].a);
                     rect.push_back(make_float4(flat[i].b.x, bits_to_float(i), 0.f, 0.f));
                 }
                 float4 rd;
-                const uint32_t w[4] = {(uint32_t)(keys[k].first + 1), keys[k].second, first, (uint32_t)members[k].size()};
+                const bool same = have_prev && prev_slot == keys[k].first;
+                const uint32_t w[4] = {(uint32_t)(keys[k].first + 1) | (same ? kRunSameXform : 0u), keys[k].second, first,
+                                       (uint32_t)members[k].size()};
                 std::memcpy(&rd, w, 16);
                 runs.push_back(rd);
+                prev_slot = keys[k].first;
+                have_prev = true;
             }
         }
         fl.n_sphere_real = (uint32_t)(stat_ids.size() + big_ids.size() + mov_ids.size());

@@ -82,9 +82,11 @@ struct DevPerlin {
 //   rect       : 2 x float4 per rect: (a0, a1, b0, b1), (k, bits(prim id), -, -), sorted into RUNS of equal
 //                (instance transform, orientation) so the object-space ray is set up once per run and the
 //                inner loop is specialised per orientation and branch-free
-//   runs       : uint4 per run: (xform slot + 1 or 0, PK_XY/XZ/YZ, first rect, count)
+//   runs       : uint4 per run: (xform slot + 1 or 0 | kRunSameXform when the previous run has the same
+//                transform, PK_XY/XZ/YZ, first rect, count); the runs of one transform are adjacent
 //   ids        : uint32 prim id per member slot, in the order sph | big | mov
 // Unused member slots have r^2 = -1 (never hit).
+constexpr uint32_t kRunSameXform = 0x80000000u;
 struct FlatLayout {
     uint32_t n_sph_groups, n_big, n_mov_groups, n_rect;
     uint32_t off_sph, off_big, off_mov, off_rect, off_ids;

@@ -351,17 +351,21 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
             }
         }
     }
-    // ---- rects: runs of equal (instance transform, orientation) ----
+    // ---- rects: runs of equal (instance transform, orientation); consecutive runs of one instance (a box = three
+    //      runs) share the object-space ray, which is therefore set up once per instance, not once per run ----
     {
         const uint4 *runs = reinterpret_cast<const uint4 *>(s + L.off_runs);
+        float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
         for (uint32_t q = 0; q < L.n_runs; ++q) {
             const uint4 run = runs[q];
-            float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
-            if (run.x) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
-                if (active) cn.add(ST_XFORM_APPS);
-                const DevXform x = sc.xforms[run.x - 1u];
-                o[0] = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; o[1] = r.oy + x.ty; o[2] = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
-                d[0] = fmaf(x.c, r.dx, -x.s * r.dz); d[2] = fmaf(x.s, r.dx, x.c * r.dz);
+            if (!(run.x & kRunSameXform)) {
+                o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; d[0] = r.dx; d[1] = r.dy; d[2] = r.dz;
+                if (run.x) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
+                    if (active) cn.add(ST_XFORM_APPS);
+                    const DevXform x = sc.xforms[run.x - 1u];
+                    o[0] = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; o[1] = r.oy + x.ty; o[2] = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
+                    d[0] = fmaf(x.c, r.dx, -x.s * r.dz); d[2] = fmaf(x.s, r.dx, x.c * r.dz);
+                }
             }
             const float4 *rp = s + L.off_rect + 2 * run.z;
             if (active) cn.add(ST_RECT_TESTS, run.w);
