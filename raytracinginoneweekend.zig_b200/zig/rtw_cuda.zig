@@ -82,6 +82,20 @@ pub extern "c" fn rtw_cuda_abi_version() u32;
 pub extern "c" fn rtw_cuda_upload_scene(ctx: *Ctx, scene: *const SceneDesc) c_int;
 pub extern "c" fn rtw_cuda_render(ctx: *Ctx, cam: *const Camera, params: *const RenderParams, rgb8_out: [*]u8, accum_out: ?[*]f32) c_int;
 
+/// rtw_stats of include/rtw_cuda.h: event counters (filled when flags & 1), timers, facts about the uploaded scene.
+pub const Stats = extern struct {
+    paths: u64, rays: u64, node_tests: u64, sphere_tests: u64, sphere_roots: u64, moving_tests: u64,
+    rect_tests: u64, rect_accepts: u64, xform_apps: u64, sphere_finalise: u64, scatter_diffuse: u64,
+    scatter_metal: u64, scatter_dielectric: u64, emit_hits: u64, tex_checker: u64, tex_image: u64,
+    tex_noise: u64, nan_pixels: u64,
+    ms_trace: f64, ms_resolve: f64, ms_upload: f64,
+    n_launches: u32, variant_used: u32, bvh_nodes: u32, bvh_depth: u32,
+    ms_bvh_build: f64,
+    bvh_builder: u32, // 0 = host binned SAH, 1 = device Morton/radix tree
+    reserved0: u32,
+};
+pub extern "c" fn rtw_cuda_stats(ctx: *Ctx, out: *Stats) c_int;
+
 pub extern "c" fn rtw_cuda_render_multi(ctxs: [*]const ?*Ctx, n_ctx: u32, cam: *const Camera, params: *const RenderParams, rgb8_out: [*]u8) c_int;
 
 pub const Error = error{ CudaUnavailable, SceneRejected, RenderFailed };
