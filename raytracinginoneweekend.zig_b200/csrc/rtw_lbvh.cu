@@ -50,9 +50,9 @@ __device__ __forceinline__ int prefix(const uint64_t *__restrict__ keys, int n, 
 }
 
 // Karras 2012: internal node i of the radix tree over sorted keys covers [lo, hi] and splits after `gamma`.
-__global__ void k_hierarchy(const uint64_t *__restrict__ keys, uint32_t ns, uint32_t max_leaf, uint2 *__restrict__ range,
+__global__ void k_hierarchy(const uint64_t *__restrict__ keys, uint32_t ns, uint2 *__restrict__ range,
                             uint32_t *__restrict__ gamma, uint32_t *__restrict__ parent_int,
-                            uint32_t *__restrict__ parent_leaf, uint32_t *__restrict__ survive) {
+                            uint32_t *__restrict__ parent_leaf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)ns;
     if (i >= n - 1) return;
@@ -78,7 +78,6 @@ __global__ void k_hierarchy(const uint64_t *__restrict__ keys, uint32_t ns, uint
     gamma[i] = (uint32_t)g;
     if (lo == g) parent_leaf[g] = (uint32_t)i; else parent_int[g] = (uint32_t)i;
     if (hi == g + 1) parent_leaf[g + 1] = (uint32_t)i; else parent_int[g + 1] = (uint32_t)i;
-    survive[i] = (uint32_t)(hi - lo + 1) > max_leaf ? 1u : 0u;
     if (i == 0) parent_int[0] = 0xFFFFFFFFu;
 }
 
@@ -100,10 +99,19 @@ __device__ __forceinline__ Box int_box(const float4 *ibox, uint32_t i, uint32_t 
     return Box{a.x, a.y, a.z, b.x, b.y, b.z};
 }
 
+__device__ __forceinline__ float half_area(const Box &b) {
+    const float dx = b.mxx - b.mnx, dy = b.mxy - b.mny, dz = b.mxz - b.mnz;
+    return fmaf(dx, dy, fmaf(dy, dz, dz * dx));
+}
+
+// Bottom-up: boxes, and which subtrees fold into one leaf.  A subtree of <= max_leaf primitives folds when the surface
+// area heuristic prefers it -- area x count against the node's own area plus the cost of its two (already optimally
+// folded) children -- the criterion of the host builder (rtw_bvh.cpp; weighting the primitive test below 1 folds more
+// and was slower: 0.75 / 0.5 / 0.35 -> 58.3 / 60.5 / 61.5 ms against 57.8).  survive[i] = 1 for nodes that stay interior.
 __global__ void k_fit(const float *__restrict__ boxes, const uint32_t *__restrict__ vals, uint32_t ns, uint32_t max_leaf,
                       const uint2 *__restrict__ range, const uint32_t *__restrict__ gamma,
                       const uint32_t *__restrict__ parent_int, const uint32_t *__restrict__ parent_leaf,
-                      unsigned int *__restrict__ arrivals, float4 *ibox) {
+                      unsigned int *__restrict__ arrivals, float4 *ibox, float *icost, uint32_t *__restrict__ survive) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= ns) return;
     uint32_t cur = parent_leaf[p];
@@ -115,10 +123,19 @@ __global__ void k_fit(const float *__restrict__ boxes, const uint32_t *__restric
         uint32_t ll = 1, lr = 1, pl = 0, pr = 0;
         const Box L = rg.x == g ? prim_box(boxes, vals[g]) : int_box(ibox, g, ll, pl);
         const Box R = rg.y == g + 1 ? prim_box(boxes, vals[g + 1]) : int_box(ibox, g + 1, lr, pr);
-        const bool folded = (rg.y - rg.x + 1) <= max_leaf;
+        const Box B{fminf(L.mnx, R.mnx), fminf(L.mny, R.mny), fminf(L.mnz, R.mnz),
+                    fmaxf(L.mxx, R.mxx), fmaxf(L.mxy, R.mxy), fmaxf(L.mxz, R.mxz)};
+        const uint32_t count = rg.y - rg.x + 1;
+        const float cl = rg.x == g ? half_area(L) : __ldcg(icost + g);
+        const float cr = rg.y == g + 1 ? half_area(R) : __ldcg(icost + g + 1);
+        const float area = half_area(B);
+        const float split_cost = area + cl + cr, leaf_cost = area * (float)count;
+        const bool folded = count <= max_leaf && !(split_cost < leaf_cost);
         const uint32_t levels = folded ? 1u : 1u + max(ll, lr), pairs = folded ? 0u : 1u + pl + pr;
-        ibox[2 * (size_t)cur] = make_float4(fminf(L.mnx, R.mnx), fminf(L.mny, R.mny), fminf(L.mnz, R.mnz), __uint_as_float(levels));
-        ibox[2 * (size_t)cur + 1] = make_float4(fmaxf(L.mxx, R.mxx), fmaxf(L.mxy, R.mxy), fmaxf(L.mxz, R.mxz), __uint_as_float(pairs));
+        icost[cur] = folded ? leaf_cost : split_cost;
+        survive[cur] = folded ? 0u : 1u;
+        ibox[2 * (size_t)cur] = make_float4(B.mnx, B.mny, B.mnz, __uint_as_float(levels));
+        ibox[2 * (size_t)cur + 1] = make_float4(B.mxx, B.mxy, B.mxz, __uint_as_float(pairs));
         __threadfence();
         cur = parent_int[cur];
     }
@@ -127,20 +144,23 @@ __global__ void k_fit(const float *__restrict__ boxes, const uint32_t *__restric
 // Pre-order position (in pairs) of the pair each surviving node emits: the left subtree directly behind its parent, the
 // right subtree behind the left one -- the layout the host builder produces, so a descent to the left stays in the
 // same or the next cache line.  Each node sums its own path to the root (depth <= ~64 steps).
+constexpr uint32_t kInsideLeaf = 0xFFFFFFFFu;
 __global__ void k_offsets(uint32_t ns, const uint2 *__restrict__ range, const uint32_t *__restrict__ gamma,
                           const uint32_t *__restrict__ parent_int, const uint32_t *__restrict__ survive,
                           const float4 *__restrict__ ibox, uint32_t *__restrict__ pair_index) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns - 1 || !survive[i]) return;
     uint32_t off = 0, c = i;
+    bool inside_leaf = false;  // an ancestor folded: this node is part of that leaf and emits nothing
     while (c != 0u) {
         const uint32_t p = parent_int[c];
         const uint32_t g = gamma[p];
+        inside_leaf |= survive[p] == 0u;
         off += 1u;
         if (c == g + 1u && range[p].x != g) off += __float_as_uint(ibox[2 * (size_t)g + 1].w);  // pairs of the left sibling
         c = p;
     }
-    pair_index[i] = off;
+    pair_index[i] = inside_leaf ? kInsideLeaf : off;
 }
 
 __device__ __forceinline__ void store_node(BvhNode *nodes, uint32_t at, const Box &b, uint32_t a, uint32_t cnt) {
@@ -156,7 +176,7 @@ __global__ void k_emit(const float *__restrict__ boxes, const uint32_t *__restri
                        const float4 *__restrict__ ibox, BvhNode *__restrict__ nodes, uint32_t root_slot, uint32_t pair_base,
                        uint32_t *__restrict__ order, uint32_t slot_base) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ns - 1 || !survive[i]) return;
+    if (i >= ns - 1 || !survive[i] || pair_index[i] == kInsideLeaf) return;
     const uint2 rg = range[i];
     const uint32_t g = gamma[i];
     const uint32_t at = pair_base + 2u * pair_index[i];
@@ -213,7 +233,7 @@ cudaError_t gather_prims(const DevPrim *src, const uint32_t *d_order, DevPrim *d
 
 namespace {
 struct ArenaLayout {
-    size_t keys0, keys1, vals0, vals1, range, gamma, pint, pleaf, surv, pair, arrivals, ibox, tmp, total, sort_bytes;
+    size_t keys0, keys1, vals0, vals1, range, gamma, pint, pleaf, surv, pair, arrivals, ibox, icost, tmp, total, sort_bytes;
 };
 cudaError_t arena_layout(uint32_t ns, ArenaLayout &a) {
     a.sort_bytes = 0;
@@ -225,7 +245,7 @@ cudaError_t arena_layout(uint32_t ns, ArenaLayout &a) {
     auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes); return at; };
     a.keys0 = take(8 * n); a.keys1 = take(8 * n); a.vals0 = take(4 * n); a.vals1 = take(4 * n);
     a.range = take(8 * n); a.gamma = take(4 * n); a.pint = take(4 * n); a.pleaf = take(4 * n);
-    a.surv = take(4 * n); a.pair = take(4 * n); a.arrivals = take(4 * n); a.ibox = take(32 * n);
+    a.surv = take(4 * n); a.pair = take(4 * n); a.arrivals = take(4 * n); a.ibox = take(32 * n); a.icost = take(4 * n);
     a.tmp = take(a.sort_bytes);
     a.total = off;
     return cudaSuccess;
@@ -254,6 +274,7 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     auto *surv = (uint32_t *)(arena + L.surv), *pair = (uint32_t *)(arena + L.pair);
     auto *arrivals = (unsigned int *)(arena + L.arrivals);
     auto *ibox = (float4 *)(arena + L.ibox);
+    auto *icost = (float *)(arena + L.icost);
     void *tmp = arena + L.tmp;
     const size_t sort_bytes = L.sort_bytes;
 
@@ -271,10 +292,10 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
     size_t tb = sort_bytes;
     if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, vals0, vals1, (int)ns, 0, 63, st)) != cudaSuccess) return done(e);
-    k_hierarchy<<<blocks, tpb, 0, st>>>(keys1, ns, max_leaf, range, gamma, pint, pleaf, surv);
+    k_hierarchy<<<blocks, tpb, 0, st>>>(keys1, ns, range, gamma, pint, pleaf);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
     if ((e = cudaMemsetAsync(arrivals, 0, 4 * n, st)) != cudaSuccess) return done(e);
-    k_fit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, max_leaf, range, gamma, pint, pleaf, arrivals, ibox);
+    k_fit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, max_leaf, range, gamma, pint, pleaf, arrivals, ibox, icost, surv);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
     k_offsets<<<blocks, tpb, 0, st>>>(ns, range, gamma, pint, surv, ibox, pair);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
