@@ -57,6 +57,25 @@ def test_enums_match_header(rtw):
     assert [val(n) for n in ("RTW_MAT_DIFFUSE", "RTW_MAT_METAL", "RTW_MAT_DIELECTRIC", "RTW_MAT_DIFFUSE_LIGHT")] == [0, 1, 2, 3]
     assert [val(n) for n in ("RTW_TEX_SOLID", "RTW_TEX_CHECKER", "RTW_TEX_NOISE", "RTW_TEX_IMAGE")] == [0, 1, 2, 3]
     assert [val(n) for n in ("RTW_VARIANT_AUTO", "RTW_VARIANT_MEGA_FLAT", "RTW_VARIANT_MEGA_BVH", "RTW_VARIANT_WAVEFRONT")] == [0, 1, 2, 3]
+    assert [val(n) for n in ("RTW_BVH_BUILDER_SAH", "RTW_BVH_BUILDER_LBVH")] == [abi.BVH_BUILDER_SAH, abi.BVH_BUILDER_LBVH]
+    assert int(re.search(r"RTW_FLAG_COUNT_EVENTS\s*=\s*(\d+)u", text).group(1)) == abi.FLAG_COUNT_EVENTS
+    assert int(re.search(r"RTW_FLAG_DETERMINISTIC\s*=\s*(\d+)u", text).group(1)) == abi.FLAG_DETERMINISTIC
+    assert int(re.search(r"#define RTW_ABI_VERSION (\d+)u", text).group(1)) == abi.RTW_ABI_VERSION
+
+
+def test_zig_mirror_keeps_the_header_field_order(rtw):
+    """zig/rtw_cuda.zig is uncompiled here (no toolchain): at least its extern structs must list the header's fields in
+    the header's order, and its ABI version must match."""
+    zig = open(os.path.join(ROOT, "raytracinginoneweekend.zig_b200", "zig", "rtw_cuda.zig")).read()
+    abi = rtw.abi
+    assert int(re.search(r"ABI_VERSION: u32 = (\d+);", zig).group(1)) == abi.RTW_ABI_VERSION
+    for zname, cls in (("Camera", abi.Camera), ("RenderParams", abi.RenderParams), ("Stats", abi.Stats),
+                       ("SceneDesc", abi.SceneDesc), ("Prim", abi.Prim)):
+        m = re.search(r"pub const " + zname + r" = extern struct \{(.*?)\n\};", zig, re.S)
+        assert m, zname
+        body = re.sub(r"//[^\n]*", "", m.group(1))
+        fields = re.findall(r"([a-z_][a-z0-9_]*)\s*:", body)
+        assert fields == [f for f, _ in cls._fields_], (zname, fields)
 
 
 def test_product_does_not_touch_the_oracle():
