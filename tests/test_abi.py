@@ -70,8 +70,9 @@ def test_zig_mirror_keeps_the_header_field_order(rtw):
     abi = rtw.abi
     assert int(re.search(r"ABI_VERSION: u32 = (\d+);", zig).group(1)) == abi.RTW_ABI_VERSION
     for zname, cls in (("Camera", abi.Camera), ("RenderParams", abi.RenderParams), ("Stats", abi.Stats),
-                       ("SceneDesc", abi.SceneDesc), ("Prim", abi.Prim)):
-        m = re.search(r"pub const " + zname + r" = extern struct \{(.*?)\n\};", zig, re.S)
+                       ("SceneDesc", abi.SceneDesc), ("Prim", abi.Prim), ("Xform", abi.Xform), ("Material", abi.Material),
+                       ("Texture", abi.Texture), ("Image", abi.Image), ("Perlin", abi.Perlin)):
+        m = re.search(r"pub const " + zname + r" = extern struct \{(.*?)\};", zig, re.S)
         assert m, zname
         body = re.sub(r"//[^\n]*", "", m.group(1))
         fields = re.findall(r"([a-z_][a-z0-9_]*)\s*:", body)
