@@ -688,4 +688,106 @@ int orc_kat_hit_record(void *h, const double *ray7, double *out12) {
     return 1;
 }
 
+// ---- unit-level hooks (pinned against the transpiled reference in tests/test_ref_pin.py; the *_given forms are
+//      what the device's unit probe is compared with) ---------------------------------------------------------
+static Ray<double> ray_of(const double *q) { return {{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, q[6]}; }
+static void ray_to(const Ray<double> &r, double *q) {
+    q[0] = r.o.x; q[1] = r.o.y; q[2] = r.o.z; q[3] = r.d.x; q[4] = r.d.y; q[5] = r.d.z; q[6] = r.time;
+}
+static void rec_to(const HitRecord<double> &rec, double *o) {
+    o[0] = rec.t; o[1] = rec.p.x; o[2] = rec.p.y; o[3] = rec.p.z;
+    o[4] = rec.normal.x; o[5] = rec.normal.y; o[6] = rec.normal.z;
+    o[7] = rec.u; o[8] = rec.v; o[9] = rec.front_face ? 1.0 : 0.0;
+    o[10] = (double)rec.prim_id; o[11] = (double)rec.material;
+}
+// n rays against world.hit (hittable.zig:47-59) with explicit [t_min, t_max]; out12 as orc_kat_hit_record
+void orc_kat_hit_records(void *h, uint32_t n, const double *rays7, double t_min, double t_max, double *out12, uint8_t *hit_mask) {
+    auto *os = (OrcScene *)h;
+    for (uint32_t i = 0; i < n; ++i) {
+        HitRecord<double> rec;
+        const bool ok = hit<double>(os->scene.world, ray_of(rays7 + 7 * (size_t)i), t_min, t_max, rec);
+        hit_mask[i] = ok ? 1 : 0;
+        if (ok) rec_to(rec, out12 + 12 * (size_t)i);
+    }
+}
+double orc_kat_perlin_noise(void *h, int perlin, const double *p) {
+    return ((OrcScene *)h)->scene.perlins[perlin].noise<double>({p[0], p[1], p[2]});
+}
+void orc_kat_perlin_tables(void *h, int perlin, double *ranvec768, uint32_t *perm768) {
+    const Perlin &pn = ((OrcScene *)h)->scene.perlins[perlin];
+    std::memcpy(ranvec768, pn.ranvec, sizeof pn.ranvec);
+    std::memcpy(perm768, pn.perm, sizeof pn.perm);
+}
+static HitRecord<double> rec_of(const double *rec10, int material) {
+    HitRecord<double> rec;
+    rec.p = {rec10[0], rec10[1], rec10[2]}; rec.normal = {rec10[3], rec10[4], rec10[5]};
+    rec.u = rec10[6]; rec.v = rec10[7]; rec.front_face = rec10[8] != 0.0; rec.t = rec10[9];
+    rec.material = material;
+    return rec;
+}
+// Material.scatter (material.zig:22-29) + emitted (:31-38) with the reference's own sampling from Rng(seed);
+// rec10 = p[3], normal[3], u, v, front_face, t.  out14 = attenuation[3], scattered ray[7], emitted[3], draws used
+int orc_kat_scatter(void *h, int material, const double *ray7, const double *rec10, uint64_t seed, double *out14) {
+    auto *os = (OrcScene *)h;
+    const HitRecord<double> rec = rec_of(rec10, material);
+    Rng g(seed);
+    V3d att{0, 0, 0};
+    Ray<double> sc{{0, 0, 0}, {0, 0, 0}, 0};
+    const bool ok = os->scene.scatter<double>(ray_of(ray7), rec, att, sc, g);
+    const V3d em = os->scene.emitted<double>(rec);
+    out14[0] = att.x; out14[1] = att.y; out14[2] = att.z;
+    ray_to(sc, out14 + 3);
+    out14[10] = em.x; out14[11] = em.y; out14[12] = em.z;
+    out14[13] = (double)g.draws;
+    return ok ? 1 : 0;
+}
+// same with the random choices supplied: vec3 = the unit vector (diffuse) / ball point (metal), xi = the uniform (dielectric)
+int orc_kat_scatter_given(void *h, int material, const double *ray7, const double *rec10, const double *vec3, double xi,
+                          double *out13) {
+    auto *os = (OrcScene *)h;
+    const HitRecord<double> rec = rec_of(rec10, material);
+    GivenSampler smp;
+    smp.vec = {vec3[0], vec3[1], vec3[2]};
+    smp.xi = xi;
+    V3d att{0, 0, 0};
+    Ray<double> sc{{0, 0, 0}, {0, 0, 0}, 0};
+    const bool ok = os->scene.scatter_s<double>(ray_of(ray7), rec, att, sc, smp);
+    const V3d em = os->scene.emitted<double>(rec);
+    out13[0] = att.x; out13[1] = att.y; out13[2] = att.z;
+    ray_to(sc, out13 + 3);
+    out13[10] = em.x; out13[11] = em.y; out13[12] = em.z;
+    return ok ? 1 : 0;
+}
+// Camera.getRay (main.zig:91-100) from Rng(seed); returns draws used
+uint64_t orc_kat_get_ray(const rtw_camera *cam, uint64_t seed, double s, double t, double *ray7) {
+    const Camera c = camera_from(cam);
+    Rng g(seed);
+    ray_to(c.get_ray<double>(g, s, t), ray7);
+    return g.draws;
+}
+// same with the lens-disk point and the time uniform supplied
+void orc_kat_get_ray_given(const rtw_camera *cam, const double *disk2, double time_xi, double s, double t, double *ray7) {
+    const Camera c = camera_from(cam);
+    GivenSampler smp;
+    smp.vec = {disk2[0], disk2[1], 0.0};
+    smp.xi = time_xi;
+    ray_to(c.get_ray_s<double>(smp, s, t), ray7);
+}
+// rayColor (main.zig:103-122) of one ray from Rng(seed): out5 = colour[3], rays traced, draws used
+void orc_kat_ray_color(void *h, const double *ray7, const double *bg3, uint32_t depth, uint64_t seed, double *out5) {
+    auto *os = (OrcScene *)h;
+    Rng g(seed);
+    Counters cn;
+    const V3d c = os->scene.ray_color<double>(ray_of(ray7), {bg3[0], bg3[1], bg3[2]}, g, depth, cn);
+    out5[0] = c.x; out5[1] = c.y; out5[2] = c.z; out5[3] = (double)cn.rays; out5[4] = (double)g.draws;
+}
+// rand.zig:22-40 from Rng(seed): which = 0 randomPointInUnitSphere, 1 randomPointInUnitDisk, 2 randomUnitVector
+void orc_kat_samplers(uint64_t seed, int which, uint32_t n, double *out3) {
+    Rng g(seed);
+    for (uint32_t i = 0; i < n; ++i) {
+        const V3d v = which == 0 ? random_in_unit_sphere<double>(g) : which == 1 ? random_in_unit_disk<double>(g) : random_unit_vector<double>(g);
+        out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+    }
+}
+
 }  // extern "C"

@@ -5,11 +5,17 @@
 // cpu_baseline / --impl reference legs may build, load or call anything in oracle/.  The
 // product (raytracinginoneweekend.zig_b200/) never includes, links or executes this code.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and
-// it cannot be compiled here (no `zig` toolchain; zigimg is fetched from the network,
-// build.zig.zon:69-72; only scene 6 type-checks).  The pins this oracle is
-// held to are the known-answer tests of SURVEY.md Appendix C (tests/test_oracle_kat.py), derived
-// from the reference's formulas, plus the Xoshiro256++ vector of Zig's own std test.
+// PINNING.  The reference ships no tests, golden vectors or fixtures and cannot be compiled here (no
+// `zig` toolchain; zigimg is fetched from the network, build.zig.zon:69-72; only scene 6 type-checks, SURVEY.md §0
+// D4), so there is no oracle/_ref binary.  What pins this restatement instead is the reference's SOURCE TEXT, executed:
+// tests/ref_transpile.py transpiles /root/reference/src/*.zig to Python at test time (same f64 statements, same order)
+// and tests/test_ref_pin.py demands bit-for-bit equality with this oracle for main() on all six scenes, every
+// Hittable.hit / boudingBox body, Aabb.hit, the materials, textures, Perlin, Camera, rayColor and the rejection
+// samplers (>= 10^4 random inputs per family); tests/golden/ref_golden.json carries the reference's outputs to machines
+// without /root/reference (tests/test_ref_golden.py).  Still NOT pinned by anything in the reference's tree: Zig std's
+// DefaultPrng / Random.float(f64) / uintLessThan and libm (restated from the published algorithms, SURVEY.md App. E;
+// the Xoshiro256++ vector of Zig's own std test is checked in tests/test_oracle_kat.py) — they only decide WHICH
+// scene seed 42 generates and which stream the CPU samples, never a statement of the path.
 //
 // Everything is templated on `Real`:
 //   Real = double  — the reference's semantics (Vec3 is 3 x f64, src/rtw/vec.zig:8-11);
@@ -205,7 +211,9 @@ struct Perlin {
                                          perm[2][(k + dk) & 255];
                     const V3<R> c{R(ranvec[idx][0]), R(ranvec[idx][1]), R(ranvec[idx][2])};
                     const R ti = R(di), tj = R(dj), tk = R(dk);
-                    const V3<R> wv{u - ti, v - tj, w - tk};
+                    // perlin.zig:77 hands the Hermite-SMOOTHED u_, v_, w_ to perlinInterp, whose weight vector
+                    // (perlin.zig:114) is therefore (u_ - i, v_ - j, w_ - k) — not the book's raw (u - i, ...)
+                    const V3<R> wv{uu - ti, vv - tj, ww - tk};
                     accum += (ti * uu + (R(1) - ti) * (R(1) - uu)) *
                              (tj * vv + (R(1) - tj) * (R(1) - vv)) *
                              (tk * ww + (R(1) - tk) * (R(1) - ww)) * V3<R>::dot(c, wv);
@@ -543,6 +551,26 @@ bool hit(const Hittable &h, const Ray<R> &r, R t_min, R t_max, HitRecord<R> &rec
 }
 
 // ------------------------------------------------------------------------------------------
+// Sources of randomness for getRay / scatter.  RngSampler = the reference's behaviour (rand.zig:13-40 on the one
+// sequential stream); GivenSampler = values supplied by a test.
+// ------------------------------------------------------------------------------------------
+struct RngSampler {
+    Rng &g;
+    double real01() { return g.real01(); }
+    template <class R> V3<R> in_unit_sphere() { return random_in_unit_sphere<R>(g); }
+    template <class R> V3<R> in_unit_disk() { return random_in_unit_disk<R>(g); }
+    template <class R> V3<R> unit_vector() { return random_unit_vector<R>(g); }
+};
+struct GivenSampler {
+    V3d vec{0, 0, 0};  // the unit vector / ball point / disk point the call will consume
+    double xi = 0;     // the uniform it will consume
+    double real01() { return xi; }
+    template <class R> V3<R> in_unit_sphere() { return vec.as<R>(); }
+    template <class R> V3<R> in_unit_disk() { return vec.as<R>(); }
+    template <class R> V3<R> unit_vector() { return vec.as<R>(); }
+};
+
+// ------------------------------------------------------------------------------------------
 // Camera — src/main.zig:40-101
 // ------------------------------------------------------------------------------------------
 struct Camera {
@@ -577,15 +605,25 @@ struct Camera {
                               .sub(lens_offset);
         return {origin.as<R>().add(lens_offset), dir, time};
     }
-    template <class R>
-    Ray<R> get_ray(Rng &g, R s, R t) const {  // main.zig:91-100
-        const V3<R> rd = random_in_unit_disk<R>(g).mul(R(lens_radius));
+    // getRay main.zig:91-100 with the source of randomness abstracted: S provides in_unit_disk() and real01().
+    // RngSampler draws them from the sequential stream exactly as the reference does; GivenSampler replays
+    // caller-supplied values (unit-level comparison with the device, whose samplers are rejection-free).
+    template <class R, class S>
+    Ray<R> get_ray_s(S &smp, R s, R t) const {
+        const V3<R> rd = smp.template in_unit_disk<R>().mul(R(lens_radius));
         const V3<R> offset = u.as<R>().mul(rd.x).add(v.as<R>().mul(rd.y));
         Ray<R> r = ray_from<R>(offset, s, t, R(0));
-        r.time = R(g.real(time0, time1));
+        r.time = R(time0 + smp.real01() * (time1 - time0));  // randomReal rand.zig:18-20
         return r;
     }
+    template <class R>
+    Ray<R> get_ray(Rng &g, R s, R t) const;
 };
+template <class R>
+inline Ray<R> Camera::get_ray(Rng &g, R s, R t) const {
+    RngSampler smp{g};
+    return get_ray_s<R>(smp, s, t);
+}
 
 // ------------------------------------------------------------------------------------------
 // Scene = world + tables
@@ -666,10 +704,15 @@ struct Scene {
 
     template <class R>
     bool scatter(const Ray<R> &r_in, const HitRecord<R> &rec, V3<R> &att, Ray<R> &out, Rng &g) const {
+        RngSampler smp{g};
+        return scatter_s<R>(r_in, rec, att, out, smp);
+    }
+    template <class R, class S>
+    bool scatter_s(const Ray<R> &r_in, const HitRecord<R> &rec, V3<R> &att, Ray<R> &out, S &smp) const {
         const Material &m = materials[rec.material];  // Material.scatter material.zig:22-29
         switch (m.kind) {
             case Material::DIFFUSE: {  // material.zig:44-52
-                V3<R> dir = rec.normal.add(random_unit_vector<R>(g));
+                V3<R> dir = rec.normal.add(smp.template unit_vector<R>());
                 if (dir.near_zero()) dir = rec.normal;
                 out = {rec.p, dir, r_in.time};
                 att = texture_value<R>(m.texture, rec.u, rec.v, rec.p);
@@ -677,7 +720,7 @@ struct Scene {
             }
             case Material::METAL: {  // material.zig:59-65 (tests the UN-fuzzed reflection, Q17)
                 const V3<R> refl = reflect<R>(r_in.d.normalized(), rec.normal);
-                out = {rec.p, refl.add(random_in_unit_sphere<R>(g).mul(R(m.param))), r_in.time};
+                out = {rec.p, refl.add(smp.template in_unit_sphere<R>().mul(R(m.param))), r_in.time};
                 att = m.albedo.as<R>();
                 return V3<R>::dot(refl, rec.normal) > R(0);
             }
@@ -689,7 +732,7 @@ struct Scene {
                 const R sin_theta = std::sqrt(R(1) - cos_theta * cos_theta);
                 const bool can_refract = ratio * sin_theta <= R(1);
                 // short-circuit: the draw happens only when refraction is possible (Q13)
-                const V3<R> dir = (can_refract && reflectance<R>(cos_theta, ratio) < R(g.real01()))
+                const V3<R> dir = (can_refract && reflectance<R>(cos_theta, ratio) < R(smp.real01()))
                                       ? refract<R>(ud, rec.normal, ratio)
                                       : reflect<R>(ud, rec.normal);
                 out = {rec.p, dir, r_in.time};

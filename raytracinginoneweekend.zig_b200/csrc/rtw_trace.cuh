@@ -579,7 +579,8 @@ __device__ __forceinline__ float perlin_noise(const DevPerlin &pn, float x, floa
                 const uint32_t idx = pn.perm[0][(i + di) & 255] ^ pn.perm[1][(j + dj) & 255] ^ pn.perm[2][(k + dk) & 255];
                 const float4 c = pn.ranvec[idx];
                 const float wx = di ? uu : 1.0f - uu, wy = dj ? vv : 1.0f - vv, wz = dk ? ww : 1.0f - ww;
-                accum += wx * wy * wz * (c.x * (u - di) + c.y * (v - dj) + c.z * (w - dk));
+                // the weight vector uses the SMOOTHED coordinates: perlin.zig:77 passes u_, v_, w_ to perlinInterp (:114)
+                accum += wx * wy * wz * (c.x * (uu - di) + c.y * (vv - dj) + c.z * (ww - dk));
             }
     return accum;
 }

@@ -74,6 +74,17 @@ def lib():
     L.orc_kat_bounding_box.argtypes = [C.c_void_p, C.c_uint32, dp, dp]
     L.orc_kat_aabb_hit.argtypes = [dp, dp, dp, C.c_double, C.c_double]
     L.orc_kat_hit_record.argtypes = [C.c_void_p, dp, dp]
+    L.orc_kat_hit_records.argtypes = [C.c_void_p, C.c_uint32, dp, C.c_double, C.c_double, dp, u8p]
+    L.orc_kat_perlin_noise.restype = C.c_double
+    L.orc_kat_perlin_noise.argtypes = [C.c_void_p, C.c_int, dp]
+    L.orc_kat_perlin_tables.argtypes = [C.c_void_p, C.c_int, dp, u32p]
+    L.orc_kat_scatter.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_uint64, dp]
+    L.orc_kat_scatter_given.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_double, dp]
+    L.orc_kat_get_ray.restype = C.c_uint64
+    L.orc_kat_get_ray.argtypes = [C.POINTER(abi.Camera), C.c_uint64, C.c_double, C.c_double, dp]
+    L.orc_kat_get_ray_given.argtypes = [C.POINTER(abi.Camera), dp, C.c_double, C.c_double, C.c_double, dp]
+    L.orc_kat_ray_color.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint64, dp]
+    L.orc_kat_samplers.argtypes = [C.c_uint64, C.c_int, C.c_uint32, dp]
     _lib = L
     return L
 
@@ -192,6 +203,62 @@ class OracleScene:
             return None
         return dict(t=out[0], p=out[1:4].copy(), normal=out[4:7].copy(), u=out[7], v=out[8],
                     front_face=bool(out[9]), prim_id=int(out[10]), material=int(out[11]))
+
+
+    def hit_records(self, rays, t_min=0.001, t_max=float("inf")):
+        """world.hit for n rays -> (hit mask[n], out[n,12] = t, p[3], n[3], u, v, front, prim, material)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        n = rays.shape[0]
+        out = np.zeros((n, 12))
+        mask = np.zeros(n, dtype=np.uint8)
+        lib().orc_kat_hit_records(self.h, n, _dp(rays), t_min, t_max, _dp(out), mask.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return mask.astype(bool), out
+
+    def perlin_noise(self, perlin, p):
+        return lib().orc_kat_perlin_noise(self.h, perlin, _dp(_d3(p)))
+
+    def perlin_turb(self, perlin, p, depth=7):
+        return lib().orc_kat_perlin_turb(self.h, perlin, _dp(_d3(p)), depth)
+
+    def perlin_tables(self, perlin):
+        rv = np.zeros((256, 3))
+        pm = np.zeros((3, 256), dtype=np.uint32)
+        lib().orc_kat_perlin_tables(self.h, perlin, _dp(rv), pm.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return rv, pm
+
+    def scatter(self, material, ray7, rec10, seed):
+        """Material.scatter + emitted with Rng(seed): dict(ok, attenuation, ray, emitted, draws)"""
+        out = np.zeros(14)
+        ok = lib().orc_kat_scatter(self.h, material, _dp(_d3(ray7)), _dp(_d3(rec10)), seed, _dp(out))
+        return dict(ok=bool(ok), attenuation=out[0:3].copy(), ray=out[3:10].copy(), emitted=out[10:13].copy(), draws=int(out[13]))
+
+    def scatter_given(self, material, ray7, rec10, vec3, xi):
+        out = np.zeros(13)
+        ok = lib().orc_kat_scatter_given(self.h, material, _dp(_d3(ray7)), _dp(_d3(rec10)), _dp(_d3(vec3)), float(xi), _dp(out))
+        return dict(ok=bool(ok), attenuation=out[0:3].copy(), ray=out[3:10].copy(), emitted=out[10:13].copy())
+
+    def ray_color(self, ray7, background, depth, seed):
+        out = np.zeros(5)
+        lib().orc_kat_ray_color(self.h, _dp(_d3(ray7)), _dp(_d3(background)), depth, seed, _dp(out))
+        return dict(color=out[0:3].copy(), rays=int(out[3]), draws=int(out[4]))
+
+
+def get_ray(cam, seed, s, t):
+    out = np.zeros(7)
+    draws = lib().orc_kat_get_ray(C.byref(cam), seed, s, t, _dp(out))
+    return out, int(draws)
+
+
+def get_ray_given(cam, disk2, time_xi, s, t):
+    out = np.zeros(7)
+    lib().orc_kat_get_ray_given(C.byref(cam), _dp(_d3(disk2)), float(time_xi), float(s), float(t), _dp(out))
+    return out
+
+
+def samplers(seed, which, n):
+    out = np.zeros((n, 3))
+    lib().orc_kat_samplers(seed, which, n, _dp(out))
+    return out
 
 
 def camera_init(look_from, look_at, vup, vfov, aspect, aperture, focus_dist=10.0, time0=0.0, time1=1.0):

@@ -267,3 +267,54 @@ def test_golden_fixtures(oracle, earth_rgba):
         assert r["rays"] == want["rays"], key
         np.testing.assert_allclose(r["accum"].sum(axis=(0, 1)), want["sum"], rtol=1e-9)
         assert int(r["rgb8"].astype(np.int64).sum()) == want["rgb8_sum"], key
+
+
+def test_perlin_known_answers(oracle):
+    """Perlin.noise hand-evaluated from perlin.zig:47-77,103-124 (NOT from the oracle).  Tables: identity permutations,
+    gradient (+1,0,0) where the table index is odd and (-1,0,0) where it is even, so in the cell [0,1)^3 the corner
+    (di,dj,dk) has gradient s(di)s(dj)s(dk)(1,0,0), s(0) = -1, s(1) = +1, and with the Hermite-smoothed U,V,W that
+    perlin.zig:77 hands to perlinInterp (whose weight vector, :114, is therefore (U-i, V-j, W-k)) the sum factorises:
+
+        noise = [-(1-U)U + U(U-1)] * (2V-1) * (2W-1) = -2U(1-U)(2V-1)(2W-1).
+
+    The book's perlin_interp (raw u in the weight vector) gives [-(1-U)u + U(u-1)] for the first factor: different
+    unless u = U.  Every number below is a dyadic rational: the expected values are exact in f64."""
+    import ctypes as C
+    import scene_util
+    from rtw_b200 import abi
+    b = scene_util.DescBuilder()
+    b.texs.append(abi.Texture(kind=abi.TEX_NOISE, a=0, b=-1, scale=4.0))
+    b.sphere((0, 0, 0), 1.0, b.diffuse(0))
+    d = b.build()
+    rv = np.zeros((256, 3))
+    rv[:, 0] = np.where(np.arange(256) & 1, 1.0, -1.0)
+    perm = np.arange(256, dtype=np.uint32)
+    pl = abi.Perlin(ranvec=rv.ctypes.data_as(C.POINTER(C.c_double)), perm_x=perm.ctypes.data_as(C.POINTER(C.c_uint32)),
+                    perm_y=perm.ctypes.data_as(C.POINTER(C.c_uint32)), perm_z=perm.ctypes.data_as(C.POINTER(C.c_uint32)))
+    arr = (abi.Perlin * 1)(pl)
+    d.n_perlins, d.perlins = 1, arr
+    s = oracle.OracleScene.from_desc(d)
+
+    def smooth(x):
+        return x * x * (3 - 2 * x)
+
+    def expect(u, v, w):
+        U, V, W = smooth(u), smooth(v), smooth(w)
+        return -2 * U * (1 - U) * (2 * V - 1) * (2 * W - 1)
+
+    assert expect(0.25, 0.25, 0.75) == 0.12462615966796875  # = 2 * (5/32)(27/32) * (11/16)^2, by hand
+    for p in ((0.25, 0.25, 0.75), (0.5, 0.25, 0.75), (0.75, 0.5, 0.125), (0.125, 0.875, 0.375)):
+        assert s.perlin_noise(0, p) == expect(*p), p
+    # the book's formula would give -[(1-U)u + U(1-u)](2V-1)(2W-1) = 0.1550903... at the first point
+    book = -((1 - smooth(0.25)) * 0.25 + smooth(0.25) * 0.75) * (2 * smooth(0.25) - 1) * (2 * smooth(0.75) - 1)
+    assert abs(book - 0.15509033203125) < 1e-15 and abs(s.perlin_noise(0, (0.25, 0.25, 0.75)) - book) > 0.03
+    # cells with negative coordinates wrap with & 255 (perlin.zig:67-69): p = (-0.75, 0.25, 0.75) has i = -1, so the x
+    # indices are 255 and 0 -> the parity pattern flips sign along x
+    assert s.perlin_noise(0, (-0.75, 0.25, 0.75)) == -expect(0.25, 0.25, 0.75)
+    # turb = |sum of 7 octaves| (perlin.zig:79-91)
+    acc, q, wgt = 0.0, np.array([0.25, 0.25, 0.75]), 1.0
+    for _ in range(7):
+        acc += wgt * s.perlin_noise(0, q)
+        wgt *= 0.5
+        q = q * 2.0
+    assert s.perlin_turb(0, (0.25, 0.25, 0.75), 7) == abs(acc)
