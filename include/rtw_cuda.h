@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 2u
+#define RTW_ABI_VERSION 3u
 
 /* ---- primitives: the leaf variants of `Hittable` (src/rtw/hittable.zig:22-33) -------- */
 enum {
@@ -208,6 +208,7 @@ typedef struct rtw_stats {
     double   ms_bvh_build;     /* BVH part of ms_upload                                         */
     uint32_t bvh_builder;      /* RTW_BVH_BUILDER_*                                             */
     uint32_t reserved0;
+    double   ms_wall;          /* rtw_cuda_render / rtw_cuda_render_multi: host wall clock of the whole call     */
 } rtw_stats;
 
 typedef struct rtw_ctx rtw_ctx;
@@ -217,6 +218,17 @@ int rtw_cuda_create(int device, rtw_ctx **out);
 void rtw_cuda_destroy(rtw_ctx *ctx);
 const char *rtw_cuda_last_error(const rtw_ctx *ctx); /* ctx may be NULL: last create error */
 uint32_t rtw_cuda_abi_version(void);
+
+/* Contexts on devices 0..n_gpus-1 (out: array of n_gpus pointers) with NVLink peer mappings between every pair
+ * enabled up front — the form rtw_cuda_render_multi wants.  (SURVEY §8b sketched `create(n_gpus)` returning ONE
+ * context; one context per device is kept instead because `torchrun`-style hosts own exactly one device per process
+ * and use rtw_cuda_create + rtw_cuda_accumulate + their own collective.)  All-or-nothing: on failure nothing is left. */
+int rtw_cuda_create_multi(uint32_t n_gpus, rtw_ctx **out);
+
+/* Tuning knobs (INTEGRATION.md lists them).  Each knob also has an environment variable of the same name, read ONCE
+ * in rtw_cuda_create; this call overrides it on a live context, value NULL restores the built-in default.  Unknown
+ * names are an error. */
+int rtw_cuda_set_option(rtw_ctx *ctx, const char *name, const char *value);
 
 /* Copy the scene, build leaf boxes (rules of the reference's `boudingBox` methods,
  * hittable.zig:133-143,203-217,305-316,358-369,411-422,491-498,598-603), build the BVH
@@ -248,9 +260,11 @@ int rtw_cuda_resolve_multi(rtw_ctx *ctx, const float *const *d_accums, uint32_t 
 
 /* Single-process multi-GPU form of rtw_cuda_render: `ctxs[i]` live on different devices and hold the SAME
  * uploaded scene.  Context i traces its share of [spp_begin, spp_end) (first spp mod n contexts take one extra
- * sample) into its own fp32 buffer; context 0's resolve kernel then reads every buffer through NVLink peer
- * mappings and sums + resolves in one pass (no separate reduction step), and the image is copied to rgb8_out
- * (HOST).  Needs peer access between device 0 and the others.  Blocking. */
+ * sample) into its own fp32 buffer; then EVERY context resolves one scanline slab of the image, its kernel reading
+ * that slab from all n buffers through NVLink peer mappings (reduction fused into the resolve, reduce-scatter
+ * shaped: each GPU ingests (n-1)/n of one buffer), and copies its rows into rgb8_out (HOST).  Needs peer access
+ * between all pairs (rtw_cuda_create_multi sets it up; otherwise it is enabled on first use).  One thread calls
+ * this for one set of contexts at a time.  Blocking; rtw_stats.ms_wall of ctxs[0] = wall clock of the call. */
 int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera *cam,
                           const rtw_render_params *params, uint8_t *rgb8_out);
 
@@ -268,6 +282,28 @@ int rtw_cuda_trace_rays(rtw_ctx *ctx, uint32_t n, const double *rays, uint32_t p
 int rtw_cuda_primary_hits(rtw_ctx *ctx, const rtw_camera *cam, uint32_t width, uint32_t height,
                           uint32_t precision, uint32_t variant, uint32_t *prim_id, double *t,
                           double *normal);
+
+/* Unit-level probes of the production STOCHASTIC device code (parity instruments).  They run the same device
+ * functions as the render kernels and return the random choices along with the result, so a host can replay the
+ * reference's statements (f64) with exactly those choices.  All buffers HOST; `params` supplies width, height (the
+ * (W-1),(H-1) denominators of main.zig:390-391) and the seed.
+ *
+ * rtw_cuda_unit_camera — Camera.getRay main.zig:91-100 + the jitter of :390-391 for n (i, j, sample) triples
+ *   (ijs: 3n uint32).  out: 14n floats = ray {o, d, time} | uniforms {ju, jv, l1, l2, tm} | lens-disk point {x, y}.
+ * rtw_cuda_unit_samplers — the rejection-free maps that replace rand.zig:22-40 for caller-supplied uniforms
+ *   (u3: 3n floats in [0,1)).  out: 8n floats = unit vector | ball point | disk point.
+ * rtw_cuda_unit_uniforms — the Philox4x32-10 draws of (pixel, sample, block) (psb: 3n uint32).  out: 8n floats =
+ *   the four 24-bit uniforms | the four raw words (bit patterns).
+ * rtw_cuda_unit_shade — one level of rayColor (main.zig:109-121) for explicit rays (7n doubles): production closest hit,
+ *   then Material.emitted/scatter (material.zig:16-110) keyed by psb (pixel, sample, bounce).  prim_id[n] (RTW_MISS = no
+ *   hit, rest of the row zero); out: 20n floats = t | scattered ray {o, d, time} | attenuation | emitted | continues
+ *   (0/1) | sample vector consumed (diffuse: unit vector, metal: ball point) | uniform consumed (dielectric) | material kind. */
+int rtw_cuda_unit_camera(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *params, uint32_t n,
+                         const uint32_t *ijs, float *out);
+int rtw_cuda_unit_samplers(rtw_ctx *ctx, uint32_t n, const float *u3, float *out);
+int rtw_cuda_unit_uniforms(rtw_ctx *ctx, const rtw_render_params *params, uint32_t n, const uint32_t *psb, float *out);
+int rtw_cuda_unit_shade(rtw_ctx *ctx, const rtw_render_params *params, uint32_t n, const double *rays,
+                        const uint32_t *psb, uint32_t *prim_id, float *out);
 
 int rtw_cuda_stats(rtw_ctx *ctx, rtw_stats *out);
 

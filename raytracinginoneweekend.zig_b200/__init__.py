@@ -5,5 +5,5 @@ the Zig host); the product is csrc/ (CUDA, sm_100a) and host/ (C++).  Import as 
 (see rtw_b200.py at the repo root: the directory name contains a dot).
 """
 from . import abi, build, cuda_lib, dist, host_lib  # noqa: F401
-from .cuda_lib import Context, RtwCudaError, render_multi  # noqa: F401
+from .cuda_lib import Context, RtwCudaError, render_multi, create_multi  # noqa: F401
 from .host_lib import HostScene, camera_init  # noqa: F401

@@ -1,7 +1,7 @@
 """ctypes mirror of include/rtw_cuda.h (field for field; checked by tests/test_abi.py)."""
 import ctypes as C
 
-RTW_ABI_VERSION = 2
+RTW_ABI_VERSION = 3
 RTW_MISS = 0xFFFFFFFF
 
 PRIM_SPHERE, PRIM_MOVING_SPHERE, PRIM_XY_RECT, PRIM_XZ_RECT, PRIM_YZ_RECT = range(5)
@@ -74,7 +74,7 @@ class Stats(C.Structure):
         ("ms_trace", C.c_double), ("ms_resolve", C.c_double), ("ms_upload", C.c_double),
         ("n_launches", C.c_uint32), ("variant_used", C.c_uint32), ("bvh_nodes", C.c_uint32),
         ("bvh_depth", C.c_uint32), ("ms_bvh_build", C.c_double), ("bvh_builder", C.c_uint32),
-        ("reserved0", C.c_uint32)]
+        ("reserved0", C.c_uint32), ("ms_wall", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -85,5 +85,6 @@ CUDA_SYMBOLS = (
     "rtw_cuda_create", "rtw_cuda_destroy", "rtw_cuda_last_error", "rtw_cuda_abi_version",
     "rtw_cuda_upload_scene", "rtw_cuda_render", "rtw_cuda_accumulate", "rtw_cuda_resolve",
     "rtw_cuda_resolve_multi", "rtw_cuda_render_multi", "rtw_cuda_trace_rays", "rtw_cuda_primary_hits", "rtw_cuda_stats",
-    "rtw_cuda_measure_fp32_peak",
+    "rtw_cuda_measure_fp32_peak", "rtw_cuda_unit_camera", "rtw_cuda_unit_samplers", "rtw_cuda_unit_uniforms", "rtw_cuda_unit_shade",
+    "rtw_cuda_create_multi", "rtw_cuda_set_option",
 )

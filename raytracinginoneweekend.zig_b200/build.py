@@ -80,6 +80,7 @@ def _build_cuda(force=False, verbose=False, extra=()):
     units = [
         ("rtw_kernels.cu", ["-Xptxas", "-v"]),          # production arithmetic: FMA contraction on
         ("rtw_wavefront.cu", []),                       # K2 wavefront schedule (same device functions)
+        ("rtw_unit.cu", []),                            # unit probes of the stochastic code (same flags as rtw_kernels.cu)
         ("rtw_probe.cu", ["-fmad=false"]),              # reference-order probe: no contraction, IEEE div/sqrt
         ("rtw_lbvh.cu", []),                            # device-side BVH build for large scenes
         ("rtw_api.cpp", []),

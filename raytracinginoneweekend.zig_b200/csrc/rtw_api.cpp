@@ -34,6 +34,7 @@ constexpr double kBigSphereRadius = 64.0;
 constexpr uint32_t kFlatAutoMax = 128;  // measured crossover on sphere scenes: flat 20 % ahead at 66 prims, level at 145, BVH 10 % ahead at 198
 constexpr uint32_t kLbvhAutoMin = 1u << 16;  // scenes at least this large build their BVH on the device
 constexpr uint32_t kFlatHardMax = 6000;  // the shared-memory image must stay under ~200 KB
+constexpr uint32_t kMaxCheckerDepth = 8;  // = the guard of the device loop in texture_value (rtw_trace.cuh)
 constexpr uint32_t kBatchSpp = 64;       // pooled kernel: a batch = one 8x4 tile x 64 samples = 2048 paths
 
 thread_local std::string g_create_error;
@@ -75,12 +76,11 @@ struct DevBuf {
 constexpr uint32_t kChunk = 1u << 15;
 inline uint32_t n_chunks_of(uint32_t n) { return (n + kChunk - 1) / kChunk; }
 template <class F>
-void for_chunks(uint32_t n, F &&fn) {
+void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
     const uint32_t nc = n_chunks_of(n);
     unsigned nt = 1;
     if (nc >= 4) {
-        nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-        if (const char *e = getenv("RTW_BUILD_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        nt = max_threads ? max_threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
         nt = std::min<unsigned>(nt, nc);
     }
     auto run = [&](unsigned t) {
@@ -93,10 +93,35 @@ void for_chunks(uint32_t n, F &&fn) {
     for (auto &t : pool) t.join();
 }
 
-// RTW_UPLOAD_TRACE=1: per-stage wall times of rtw_cuda_upload_scene on stderr
+// Tuning knobs.  Each has an environment variable of the same name, read ONCE in rtw_cuda_create (never on the render
+// path); rtw_cuda_set_option changes one on a live context.
+const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
+                                    "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE", "RTW_BVH_WIDE",
+                                    "RTW_FLAT_REGEN", "RTW_BOX_PRIMS"};
+struct Options {
+    std::map<std::string, std::string> v;
+    const char *get(const char *name) const {
+        auto it = v.find(name);
+        return it == v.end() ? nullptr : it->second.c_str();
+    }
+    long num(const char *name, long dflt) const {
+        const char *e = get(name);
+        return e && *e ? atol(e) : dflt;
+    }
+    static bool known(const char *name) {
+        for (const char *k : kOptionNames) if (std::strcmp(k, name) == 0) return true;
+        return false;
+    }
+    void read_env() {
+        for (const char *k : kOptionNames) if (const char *e = getenv(k)) v[k] = e;
+    }
+};
+
+// option RTW_UPLOAD_TRACE=1: per-stage wall times of rtw_cuda_upload_scene on stderr
 struct Laps {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    const bool on = getenv("RTW_UPLOAD_TRACE") != nullptr;
+    bool on = false;
+    explicit Laps(bool enabled) : on(enabled) {}
     void lap(const char *what) {
         if (!on) return;
         const auto t1 = std::chrono::steady_clock::now();
@@ -113,7 +138,13 @@ struct rtw_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {};
+    cudaEvent_t ev_launch = nullptr;   // end of the last accumulate launch: the next one (any stream) is ordered after it
+    cudaEvent_t ev_trace = nullptr;    // render_multi: "this device's samples are in its buffer"
+    bool launch_recorded = false;
     bool have_scene = false;
+    Options opt;
+    std::vector<int> peers_enabled;    // devices whose memory this context's device can already map
+    unsigned build_threads() const { return (unsigned)std::max(0l, opt.num("RTW_BUILD_THREADS", 0)); }
 
     DevBuf<DevPrim> prims_flat, prims_bvh;
     DevBuf<float4> flat_blob;
@@ -191,11 +222,16 @@ Box3d leaf_box(const rtw_scene_desc *s, const rtw_prim &p) {
         b.mn[0] = x0; b.mn[1] = y0; b.mn[2] = z0; b.mx[0] = x1; b.mx[1] = y1; b.mx[2] = z1;
     };
     switch (p.kind) {
-        case RTW_PRIM_SPHERE:
-            set(p.v[0] - p.v[3], p.v[1] - p.v[3], p.v[2] - p.v[3], p.v[0] + p.v[3], p.v[1] + p.v[3], p.v[2] + p.v[3]);
+        // A negative radius is legal in the reference (the hollow-glass idiom: Sphere.hit uses r*r and divides by r,
+        // hittable.zig:99,120, so the normal flips).  Its boudingBox (hittable.zig:136-141) would come out inverted;
+        // the box a BVH needs is the one of |r|.
+        case RTW_PRIM_SPHERE: {
+            const double r = std::fabs(p.v[3]);
+            set(p.v[0] - r, p.v[1] - r, p.v[2] - r, p.v[0] + r, p.v[1] + r, p.v[2] + r);
             break;
+        }
         case RTW_PRIM_MOVING_SPHERE: {
-            const double r = p.v[8];
+            const double r = std::fabs(p.v[8]);
             for (int a = 0; a < 3; ++a) {
                 const double c0 = p.v[a], c1 = p.v[3 + a];
                 const double o0 = c0 + (c1 - c0) * ((s->time0 - p.v[6]) / (p.v[7] - p.v[6]));
@@ -267,6 +303,11 @@ DevXform compose_chain(const rtw_scene_desc *s, int x) {
 int validate(rtw_ctx *ctx, const rtw_scene_desc *s) {
     if (!s) return fail(ctx, 1, "scene is null");
     if (s->n_prims && !s->prims) return fail(ctx, 1, "prims is null");
+    if (s->n_xforms && !s->xforms) return fail(ctx, 1, "xforms is null");
+    if (s->n_materials && !s->materials) return fail(ctx, 1, "materials is null");
+    if (s->n_textures && !s->textures) return fail(ctx, 1, "textures is null");
+    if (s->n_images && !s->images) return fail(ctx, 1, "images is null");
+    if (s->n_perlins && !s->perlins) return fail(ctx, 1, "perlins is null");
     if (!(s->time1 >= s->time0)) return fail(ctx, 1, "time1 < time0");
     for (uint32_t i = 0; i < s->n_xforms; ++i) {
         const rtw_xform &x = s->xforms[i];
@@ -300,8 +341,26 @@ int validate(rtw_ctx *ctx, const rtw_scene_desc *s) {
         if (t.kind == RTW_TEX_NOISE && (t.a < 0 || t.a >= (int)s->n_perlins)) return fail(ctx, 1, "texture %u: perlin out of range", i);
         if (t.kind == RTW_TEX_IMAGE && (t.a < 0 || t.a >= (int)s->n_images)) return fail(ctx, 1, "texture %u: image out of range", i);
     }
+    // checker children are textures themselves (texture.zig:59-60): the graph must be acyclic and no deeper than the
+    // device loop follows (kMaxCheckerDepth levels of checker above a non-checker texture)
+    for (uint32_t i = 0; i < s->n_textures; ++i) {
+        if (s->textures[i].kind != RTW_TEX_CHECKER) continue;
+        std::vector<std::pair<int, uint32_t>> st{{(int)i, 1u}};
+        uint64_t visited = 0;
+        while (!st.empty()) {
+            const auto [t, depth] = st.back();
+            st.pop_back();
+            if (s->textures[t].kind != RTW_TEX_CHECKER) continue;
+            if (depth > kMaxCheckerDepth) return fail(ctx, 1, "texture %u: checker nesting deeper than %u (or cyclic)", i, kMaxCheckerDepth);
+            if (++visited > 4096) return fail(ctx, 1, "texture %u: checker graph too large", i);
+            st.push_back({s->textures[t].a, depth + 1});
+            st.push_back({s->textures[t].b, depth + 1});
+        }
+    }
     for (uint32_t i = 0; i < s->n_images; ++i)
         if (!s->images[i].rgba8 || !s->images[i].width || !s->images[i].height) return fail(ctx, 1, "image %u: empty", i);
+    for (uint32_t i = 0; i < s->n_perlins; ++i)
+        if (!s->perlins[i].ranvec || !s->perlins[i].perm_x || !s->perlins[i].perm_y || !s->perlins[i].perm_z) return fail(ctx, 1, "perlin %u: null table", i);
     return 0;
 }
 
@@ -362,6 +421,12 @@ int rtw_cuda_create(int device, rtw_ctx **out) {
     if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "stream create failed"); }
     for (auto &ev : ctx->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return fail(nullptr, 2, "event create failed"); }
+    if (cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, 2, "event create failed");
+    }
+    ctx->opt.read_env();  // the only place the environment is read
     if (ctx->tile_counter.alloc(1) != cudaSuccess || ctx->stat_counters.alloc(ST_COUNT) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, 2, "device allocation failed");
@@ -386,8 +451,56 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
     ctx->lbvh_boxes.release(); ctx->lbvh_ids.release(); ctx->lbvh_arena.release();
     ctx->accum.release(); ctx->rgb8.release(); ctx->tile_counter.release(); ctx->stat_counters.release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_launch) cudaEventDestroy(ctx->ev_launch);
+    if (ctx->ev_trace) cudaEventDestroy(ctx->ev_trace);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int rtw_cuda_set_option(rtw_ctx *ctx, const char *name, const char *value) {
+    if (!ctx || !name) return fail(ctx, 1, "null argument");
+    if (!Options::known(name)) return fail(ctx, 1, "unknown option %s", name);
+    if (value) ctx->opt.v[name] = value; else ctx->opt.v.erase(name);
+    return 0;
+}
+
+// Map every other context's device into `ctx`'s device (NVLink peer access), once.
+static int enable_peers(rtw_ctx *ctx, rtw_ctx *const *ctxs, uint32_t n_ctx) {
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < n_ctx; ++i) {
+        const int dev = ctxs[i]->device;
+        if (dev == ctx->device || std::find(ctx->peers_enabled.begin(), ctx->peers_enabled.end(), dev) != ctx->peers_enabled.end()) continue;
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->device, dev));
+        if (!can) return fail(ctx, 3, "device %d cannot map device %d's memory (no peer access)", ctx->device, dev);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, 2, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        ctx->peers_enabled.push_back(dev);
+    }
+    return 0;
+}
+
+int rtw_cuda_create_multi(uint32_t n_gpus, rtw_ctx **out) {
+    if (!out) return fail(nullptr, 1, "out is null");
+    if (n_gpus == 0 || n_gpus > kMaxResolveBufs) return fail(nullptr, 1, "n_gpus must be 1..%u", kMaxResolveBufs);
+    for (uint32_t i = 0; i < n_gpus; ++i) out[i] = nullptr;
+    for (uint32_t i = 0; i < n_gpus; ++i) {
+        if (int rc = rtw_cuda_create((int)i, &out[i])) {
+            for (uint32_t k = 0; k < i; ++k) { rtw_cuda_destroy(out[k]); out[k] = nullptr; }
+            return rc;
+        }
+    }
+    // all-pairs peer mappings now, not inside the first timed frame: the slab-parallel resolve of rtw_cuda_render_multi
+    // has every GPU read every other GPU's buffer
+    for (uint32_t i = 0; i < n_gpus && n_gpus > 1; ++i) {
+        if (int rc = enable_peers(out[i], out, n_gpus)) {
+            g_create_error = out[i]->err;
+            for (uint32_t k = 0; k < n_gpus; ++k) { rtw_cuda_destroy(out[k]); out[k] = nullptr; }
+            return rc;
+        }
+    }
+    return 0;
 }
 
 // Device-side BVH build (rtw_lbvh.cu) into ctx->nodes / bvh_prim_id / prims_bvh; ctx->prims_flat must be uploaded.
@@ -399,7 +512,8 @@ void rtw_cuda_destroy(rtw_ctx *ctx) {
 static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, uint32_t leaf_max, uint32_t *n_nodes,
                                uint32_t *depth, bool *built) {
     *built = false;
-    Laps laps;
+    Laps laps(ctx->opt.get("RTW_UPLOAD_TRACE") != nullptr);
+    const unsigned bt = ctx->build_threads();
     const uint32_t n = (uint32_t)boxes.size();
     std::vector<float> fb(6 * (size_t)n);
     struct Part {
@@ -416,7 +530,7 @@ static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, ui
         }
     };
     std::vector<Part> parts(n_chunks_of(n));
-    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+    for_chunks(n, bt, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
         Part pt;
         for (uint32_t i = lo; i < hi; ++i) {
             float *b = &fb[6 * (size_t)i];
@@ -435,7 +549,7 @@ static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, ui
     if (!all.finite) return 0;  // non-finite boxes: leave them to the host builder
     const float spread = std::max(all.cmx[0] - all.cmn[0], std::max(all.cmx[1] - all.cmn[1], all.cmx[2] - all.cmn[2]));
     // second pass: split off the big ones, Morton grid over the centroids of what is left
-    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+    for_chunks(n, bt, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
         Part &pt = parts[chunk];
         pt = Part{};
         for (uint32_t i = lo; i < hi; ++i) {
@@ -472,7 +586,7 @@ static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, ui
     if (nb) {
         std::vector<Box3d> bb(nb);
         for (uint32_t k = 0; k < nb; ++k) bb[k] = boxes[big_ids[k]];
-        big = build_bvh(bb, leaf_max);
+        big = build_bvh(bb, leaf_max, bt);
         for (uint32_t k = 0; k < nb; ++k) big_order[k] = big_ids[big.order[k]];
         const uint32_t B = (uint32_t)big.nodes.size();  // [0] root, [1] pad, pairs from 2
         head.assign((size_t)B + 2, BvhNode{0, 0, 0, 0, 0, 0, 0, 0});
@@ -525,7 +639,8 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     // Instanced spheres (Translate / RotateY around a sphere): a rigid transform keeps a sphere a sphere, so they
     // are lowered to world-space spheres; the chain is kept only for the texture coordinates (getSphereUv works on
     // the object-space normal, hittable.zig:127).  `wprims` = the prims with such centres moved to world space.
-    Laps laps;
+    Laps laps(ctx->opt.get("RTW_UPLOAD_TRACE") != nullptr);
+    const unsigned bt = ctx->build_threads();
     std::vector<rtw_prim> wprims = std::move(ctx->host_prims);  // storage of the previous scene's copy, if any
     wprims.resize(n);
     std::vector<Box3d> &boxes = ctx->scratch_boxes;
@@ -533,7 +648,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     // reference point for big spheres: centroid of the centres of everything that is not big (summed per fixed
     // chunk, chunks in order: the same bits on every machine)
     std::vector<std::array<double, 4>> cen_part(n_chunks_of(n), std::array<double, 4>{0, 0, 0, 0});
-    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+    for_chunks(n, bt, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
         std::array<double, 4> acc{0, 0, 0, 0};
         for (uint32_t i = lo; i < hi; ++i) {
             rtw_prim &p = wprims[i];
@@ -553,7 +668,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             } else {
                 boxes[i] = leaf_box(s, s->prims[i]);
             }
-            if (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius) continue;
+            if (p.kind == RTW_PRIM_SPHERE && std::fabs(p.v[3]) >= kBigSphereRadius) continue;
             for (int a = 0; a < 3; ++a) acc[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
             acc[3] += 1.0;
         }
@@ -594,14 +709,14 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
             d.b = make_float4(0.f, 0.f, 0.f, 0.f);
             meta = PK_SPHERE;
-            if (p.v[3] >= kBigSphereRadius && bigs.size() < 0xFFEu) {
+            if (std::fabs(p.v[3]) >= kBigSphereRadius && bigs.size() < 0xFFEu) {
                 // q = point of the sphere surface nearest the scene's centre of interest
                 double dir[3] = {cen[0] - p.v[0], cen[1] - p.v[1], cen[2] - p.v[2]};
                 double len = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
                 if (!(len > 0)) { dir[0] = 0; dir[1] = 1; dir[2] = 0; len = 1; }
                 // the device works from the fp32-rounded centre and q: keep the identities exact in f64
                 const double cf[3] = {(double)(float)p.v[0], (double)(float)p.v[1], (double)(float)p.v[2]};
-                const double rf = (double)(float)p.v[3];
+                const double rf = std::fabs((double)(float)p.v[3]);
                 DevBigSphere g{};
                 double q[3], m[3], mm = 0;
                 for (int a = 0; a < 3; ++a) q[a] = (double)(float)(cf[a] + dir[a] / len * rf);
@@ -638,10 +753,10 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         return true;
     };
     std::vector<std::vector<uint32_t>> special(n_chunks_of(n));
-    for_chunks(n, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
+    for_chunks(n, bt, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
         for (uint32_t i = lo; i < hi; ++i) {
             const rtw_prim &p = wprims[i];
-            if (p.xform >= 0 || (p.kind == RTW_PRIM_SPHERE && p.v[3] >= kBigSphereRadius)) special[chunk].push_back(i);
+            if (p.xform >= 0 || (p.kind == RTW_PRIM_SPHERE && std::fabs(p.v[3]) >= kBigSphereRadius)) special[chunk].push_back(i);
             else lower(i);
         }
     });
@@ -655,11 +770,11 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     // Morton/Karras build on the device (rtw_lbvh.cu), with the few primitives that dwarf the rest (the ground
     // sphere) kept out of the Morton order and grafted next to the root as their own host-built subtree.
     uint32_t leaf_max = 4;
-    if (const char *e = getenv("RTW_BVH_LEAF_MAX")) leaf_max = (uint32_t)std::max(1, std::min(15, atoi(e)));  // 4-bit count in node refs
+    leaf_max = (uint32_t)std::max(1l, std::min(15l, ctx->opt.num("RTW_BVH_LEAF_MAX", leaf_max)));  // 4-bit count in node refs
     CK(ctx->prims_flat.upload(flat));
     const auto t_bvh = std::chrono::steady_clock::now();
     bool use_lbvh = n >= kLbvhAutoMin;
-    if (const char *e = getenv("RTW_BVH_BUILDER")) use_lbvh = std::strcmp(e, "lbvh") == 0 && n >= 64;
+    if (const char *e = ctx->opt.get("RTW_BVH_BUILDER")) use_lbvh = std::strcmp(e, "lbvh") == 0 && n >= 64;
     uint32_t bvh_n_nodes = 0, bvh_depth = 0;
     bool bvh_root_is_leaf = false, bvh_on_device = false;
     if (use_lbvh) {
@@ -667,7 +782,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         if (int rc = build_bvh_on_device(ctx, boxes, leaf_max, &bvh_n_nodes, &bvh_depth, &bvh_on_device)) return rc;
     }
     if (!bvh_on_device) {
-        BvhResult bvh = build_bvh(boxes, leaf_max);
+        BvhResult bvh = build_bvh(boxes, leaf_max, bt);
         if (bvh.depth > (uint32_t)64) return fail(ctx, 2, "BVH depth %u exceeds the traversal stack", bvh.depth);
         std::vector<DevPrim> leaf_order(n);
         for (uint32_t k = 0; k < n; ++k) leaf_order[k] = flat[bvh.order[k]];
@@ -729,10 +844,10 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         // sphere centre of prim i at time t (f64)
         auto centre_at = [&](uint32_t i, double t, double c[3]) {
             const rtw_prim &p = wprims[i];
-            if (p.kind == RTW_PRIM_SPHERE) { c[0] = p.v[0]; c[1] = p.v[1]; c[2] = p.v[2]; return p.v[3]; }
+            if (p.kind == RTW_PRIM_SPHERE) { c[0] = p.v[0]; c[1] = p.v[1]; c[2] = p.v[2]; return std::fabs(p.v[3]); }
             const double u = (t - p.v[6]) / (p.v[7] - p.v[6]);
             for (int a = 0; a < 3; ++a) c[a] = p.v[a] + (p.v[3 + a] - p.v[a]) * u;
-            return p.v[8];
+            return std::fabs(p.v[8]);
         };
         auto bound_of = [&](const std::vector<uint32_t> &m) {
             double cen[3] = {0, 0, 0};
@@ -925,6 +1040,22 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     return 0;
 }
 
+// the launch-independent part of DevRender: image size, sample range, seed -> Philox round keys, background
+static DevRender base_render(const rtw_render_params *p) {
+    DevRender rp{};
+    rp.width = p->width; rp.height = p->height;
+    rp.spp_begin = p->spp_begin; rp.spp_end = p->spp_end;
+    rp.max_depth = p->max_depth;
+    rp.seed_lo = (uint32_t)p->seed; rp.seed_hi = (uint32_t)(p->seed >> 32);
+    for (uint32_t i = 0; i < 10; ++i) {
+        rp.philox_keys[2 * i] = rp.seed_lo + i * 0x9E3779B9u;
+        rp.philox_keys[2 * i + 1] = rp.seed_hi + i * 0xBB67AE85u;
+    }
+    rp.bg_r = (float)p->background[0]; rp.bg_g = (float)p->background[1]; rp.bg_b = (float)p->background[2];
+    rp.inv_wm1 = (float)(1.0 / ((double)p->width - 1.0)); rp.inv_hm1 = (float)(1.0 / ((double)p->height - 1.0));
+    return rp;
+}
+
 static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *p, float *d_accum,
                            cudaStream_t st, bool timed) {
     if (!ctx) return fail(nullptr, 1, "ctx is null");
@@ -938,17 +1069,9 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     CK(cudaSetDevice(ctx->device));
     const bool stats = (p->flags & RTW_FLAG_COUNT_EVENTS) != 0;
 
-    DevRender rp{};
-    rp.width = p->width; rp.height = p->height;
-    rp.spp_begin = p->spp_begin; rp.spp_end = p->spp_end;
-    rp.max_depth = p->max_depth;
-    rp.seed_lo = (uint32_t)p->seed; rp.seed_hi = (uint32_t)(p->seed >> 32);
-    for (uint32_t i = 0; i < 10; ++i) {
-        rp.philox_keys[2 * i] = rp.seed_lo + i * 0x9E3779B9u;
-        rp.philox_keys[2 * i + 1] = rp.seed_hi + i * 0xBB67AE85u;
-    }
-    rp.bg_r = (float)p->background[0]; rp.bg_g = (float)p->background[1]; rp.bg_b = (float)p->background[2];
-    rp.inv_wm1 = (float)(1.0 / ((double)p->width - 1.0)); rp.inv_hm1 = (float)(1.0 / ((double)p->height - 1.0));
+    if (p->variant == RTW_VARIANT_WAVEFRONT && (p->max_depth > 63 || p->spp_end > (1u << 26)))
+        return fail(ctx, 1, "wavefront variant packs (sample, bounce) into 26 + 6 bits: max_depth <= 63 and spp_end <= 2^26");
+    DevRender rp = base_render(p);
     rp.accum = reinterpret_cast<float4 *>(d_accum);
     rp.tile_counter = ctx->tile_counter.p;
     rp.stats = ctx->stat_counters.p;
@@ -957,7 +1080,7 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
 
     // RTW_FLAG_DETERMINISTIC (or RTW_SPP_CHUNK=0): lane-owns-pixel kernel, one chunk, fixed summation order.
     // Default: pooled kernel (warp-level path queue + one vector atomic per path).
-    const char *env = getenv("RTW_SPP_CHUNK");
+    const char *env = ctx->opt.get("RTW_SPP_CHUNK");
     const bool env_set = env && *env;
     const bool pooled = !(p->flags & RTW_FLAG_DETERMINISTIC) && !env_set;
     const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
@@ -981,26 +1104,40 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
         const uint64_t warps = (uint64_t)grid * 4, want = warps * 24;
         const uint64_t sblocks_wanted = (want + rp.n_tiles - 1) / rp.n_tiles;
         if (sblocks_wanted > 1) batch_spp = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(kBatchSpp, spp / sblocks_wanted));
-        if (const char *e = getenv("RTW_BATCH_SPP")) batch_spp = (uint32_t)std::max(1, std::min(4096, atoi(e)));
+        if (ctx->opt.get("RTW_BATCH_SPP")) batch_spp = (uint32_t)std::max(1l, std::min(4096l, ctx->opt.num("RTW_BATCH_SPP", batch_spp)));
     }
     rp.batch_spp = batch_spp;
     rp.n_sblocks = (spp + batch_spp - 1) / batch_spp;
     if ((uint64_t)rp.n_sblocks * rp.n_tiles > 0xFFFFFFF0ull) return fail(ctx, 1, "too many path batches for one launch");
     rp.n_batches = rp.n_sblocks * rp.n_tiles;
     rp.service_threshold = 20; rp.steps_per_round = 2; rp.leaf_threshold = 8;  // tuned on the 485-sphere scene
-    if (const char *e = getenv("RTW_BVH_LEAF")) rp.leaf_threshold = (uint32_t)std::max(1, std::min(32, atoi(e)));
-    if (const char *e = getenv("RTW_BVH_THRESH")) rp.service_threshold = (uint32_t)std::max(1, std::min(32, atoi(e)));
-    if (const char *e = getenv("RTW_BVH_STEPS")) rp.steps_per_round = (uint32_t)std::max(1, std::min(64, atoi(e)));
+    rp.leaf_threshold = (uint32_t)std::max(1l, std::min(32l, ctx->opt.num("RTW_BVH_LEAF", rp.leaf_threshold)));
+    rp.service_threshold = (uint32_t)std::max(1l, std::min(32l, ctx->opt.num("RTW_BVH_THRESH", rp.service_threshold)));
+    rp.steps_per_round = (uint32_t)std::max(1l, std::min(64l, ctx->opt.num("RTW_BVH_STEPS", rp.steps_per_round)));
 
     if (spp == 0) { ctx->stats.n_launches = 0; return 0; }
+    // One work queue and one set of event counters per context: launches of one context are ordered ON THE DEVICE, whatever
+    // streams the caller uses (a second rtw_cuda_accumulate on another stream waits for the first; it does not race).
+    if (ctx->launch_recorded) CK(cudaStreamWaitEvent(st, ctx->ev_launch, 0));
     if (stats) CK(cudaMemsetAsync(ctx->stat_counters.p, 0, ST_COUNT * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned int), st));
     const DevCamera dc = lower_camera(cam);
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
+    if (p->max_depth == 0) {
+        // rayColor returns black before intersecting anything when depth == 0 (main.zig:105-108): every sample
+        // contributes (0, 0, 0); only the sample count moves
+        CK(launch_add_samples(rp.accum, p->width * p->height, (float)spp, st));
+        if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaEventRecord(ctx->ev_launch, st));
+        ctx->launch_recorded = true;
+        ctx->stats.n_launches = 1;
+        ctx->stats.variant_used = p->variant;
+        return 0;
+    }
     if (p->variant == RTW_VARIANT_WAVEFRONT) {
         // K2: host loop of generate / extend / shade launches over the path-state slots (blocks the caller)
         uint32_t slots = 1u << 21;
-        if (const char *e = getenv("RTW_WF_SLOTS")) slots = (uint32_t)std::max(128l, atol(e));
+        slots = (uint32_t)std::max(128l, ctx->opt.num("RTW_WF_SLOTS", slots));
         slots = (slots + 127u) & ~127u;
         if (ctx->wf_slots != slots) {
             CK(ctx->wf_ro.alloc(slots)); CK(ctx->wf_rd.alloc(slots)); CK(ctx->wf_beta.alloc(slots)); CK(ctx->wf_rad.alloc(slots));
@@ -1016,12 +1153,16 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
         uint32_t nl = 0;
         CK(wavefront_accumulate(ws, variant, stats, ctx->scene, dc, rp, ctx->n_sms, ctx->wf_host_counters, st, &nl));
         if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaEventRecord(ctx->ev_launch, st));
+        ctx->launch_recorded = true;
         ctx->stats.n_launches = nl;
         ctx->stats.variant_used = RTW_VARIANT_WAVEFRONT;
         return 0;
     }
     CK(launch_megakernel(variant, stats, pooled, ctx->scene, dc, rp, grid, st));
     if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaEventRecord(ctx->ev_launch, st));
+    ctx->launch_recorded = true;
     ctx->stats.n_launches = 1;
     ctx->stats.variant_used = variant == VAR_FLAT ? RTW_VARIANT_MEGA_FLAT : RTW_VARIANT_MEGA_BVH;
     return 0;
@@ -1056,6 +1197,7 @@ int rtw_cuda_resolve_multi(rtw_ctx *ctx, const float *const *d_accums, uint32_t 
         a.bufs[i] = reinterpret_cast<const float4 *>(d_accums[i]);
     }
     a.n_bufs = n_bufs; a.width = width; a.height = height;
+    a.row_begin = 0; a.row_end = height;
     a.scale = 1.0f / (float)spp_total;
     a.rgb8 = d_rgb8;
     a.nan_counter = ctx->stat_counters.p + ST_NAN_PIXELS;
@@ -1072,6 +1214,7 @@ int rtw_cuda_resolve(rtw_ctx *ctx, const float *d_accum, uint32_t width, uint32_
 
 int rtw_cuda_render(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *p, uint8_t *rgb8_out, float *accum_out) {
     if (!ctx) return fail(nullptr, 1, "ctx is null");
+    const auto t_begin = std::chrono::steady_clock::now();
     if (!p || !rgb8_out) return fail(ctx, 1, "null argument");
     if (p->width == 0 || p->height == 0) return fail(ctx, 1, "empty image");
     CK(cudaSetDevice(ctx->device));
@@ -1104,13 +1247,38 @@ int rtw_cuda_render(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params
         ctx->stats.ms_bvh_build = keep.ms_bvh_build; ctx->stats.bvh_builder = keep.bvh_builder;
         ctx->stats.paths = (uint64_t)npx * spp;
     }
+    ctx->stats.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return 0;
 }
 
+// Resolve rows [row_begin, row_end) of the sum of `bufs` on `ctx`'s device into its rgb8 buffer (device pointers).
+static int resolve_slab(rtw_ctx *ctx, const float *const *bufs, uint32_t n_bufs, uint32_t width, uint32_t height, uint32_t row_begin,
+                        uint32_t row_end, uint32_t spp_total, uint8_t *d_rgb8, cudaStream_t st) {
+    ResolveArgs a{};
+    for (uint32_t i = 0; i < n_bufs; ++i) a.bufs[i] = reinterpret_cast<const float4 *>(bufs[i]);
+    a.n_bufs = n_bufs; a.width = width; a.height = height;
+    a.row_begin = row_begin; a.row_end = row_end;
+    a.scale = 1.0f / (float)spp_total;
+    a.rgb8 = d_rgb8;
+    a.nan_counter = ctx->stat_counters.p + ST_NAN_PIXELS;
+    CK(cudaMemsetAsync(a.nan_counter, 0, sizeof(unsigned long long), st));
+    CK(launch_resolve(a, st));
+    return 0;
+}
+
+// Multi-GPU frame in one process.  Sample split as SURVEY §8(e): context i traces its share of the sample indices of
+// EVERY pixel into its own fp32 buffer.  The exchange is reduce-scatter shaped and fused with the resolve: GPU g owns
+// the scanline slab g, its resolve kernel reads that slab from all N buffers — its own from HBM, N-1 over NVLink peer
+// mappings — sums, quantises and writes its rows of the image, and copies them straight into the caller's host buffer.
+// Every GPU therefore ingests (N-1)/N of ONE buffer (round 1 had GPU 0 ingest N-1 whole buffers), all links carry
+// traffic at once, and the N device-to-host copies run in parallel.  Cross-device ordering is by events (each resolve
+// waits for every trace), the host blocks once at the end.  stats: ms_wall = host wall clock of the whole call,
+// ms_trace / ms_resolve = device 0's kernel times.
 int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera *cam, const rtw_render_params *p,
                           uint8_t *rgb8_out) {
     if (!ctxs || n_ctx == 0 || !ctxs[0]) return fail(nullptr, 1, "no contexts");
     rtw_ctx *ctx = ctxs[0];
+    const auto t_begin = std::chrono::steady_clock::now();
     if (n_ctx > kMaxResolveBufs) return fail(ctx, 1, "at most %u contexts", kMaxResolveBufs);
     if (!cam || !p || !rgb8_out) return fail(ctx, 1, "null argument");
     if (p->variant == RTW_VARIANT_WAVEFRONT) return fail(ctx, 1, "render_multi runs the megakernel variants only");
@@ -1120,10 +1288,15 @@ int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera
     const uint32_t spp_total = p->spp_total ? p->spp_total : spp;
     const float *bufs[kMaxResolveBufs];
     for (uint32_t i = 0; i < n_ctx; ++i) {
-        rtw_ctx *c = ctxs[i];
-        if (!c) return fail(ctx, 1, "context %u is null", i);
+        if (!ctxs[i]) return fail(ctx, 1, "context %u is null", i);
         for (uint32_t k = 0; k < i; ++k)
-            if (ctxs[k]->device == c->device) return fail(ctx, 1, "contexts %u and %u share device %d", k, i, c->device);
+            if (ctxs[k]->device == ctxs[i]->device) return fail(ctx, 1, "contexts %u and %u share device %d", k, i, ctxs[i]->device);
+    }
+    // peer mappings: already there after rtw_cuda_create_multi; contexts created one by one get them here, once
+    for (uint32_t i = 0; i < n_ctx && n_ctx > 1; ++i)
+        if (int rc = enable_peers(ctxs[i], ctxs, n_ctx)) { if (ctxs[i] != ctx) ctx->err = ctxs[i]->err; return rc; }
+    for (uint32_t i = 0; i < n_ctx; ++i) {
+        rtw_ctx *c = ctxs[i];
         if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, 2, "cudaSetDevice(%d) failed", c->device);
         if (c->accum.n != npx) {
             if (c->accum.alloc(npx) != cudaSuccess || c->rgb8.alloc(npx * 3) != cudaSuccess) return fail(ctx, 2, "allocation failed on device %d", c->device);
@@ -1137,32 +1310,44 @@ int rtw_cuda_render_multi(rtw_ctx *const *ctxs, uint32_t n_ctx, const rtw_camera
             if (c != ctx) ctx->err = c->err;
             return rc;
         }
+        if (cudaEventRecord(c->ev_trace, c->stream) != cudaSuccess) return fail(ctx, 2, "event record failed on device %d", c->device);
         bufs[i] = reinterpret_cast<const float *>(c->accum.p);
     }
+    // slab g = scanlines [g H / N, (g+1) H / N); image rows are flipped (main.zig:396), so slab g lands in the host
+    // buffer at rows [H - j1, H - j0)
+    for (uint32_t g = 0; g < n_ctx; ++g) {
+        rtw_ctx *c = ctxs[g];
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, 2, "cudaSetDevice(%d) failed", c->device);
+        for (uint32_t k = 0; k < n_ctx; ++k)
+            if (k != g && cudaStreamWaitEvent(c->stream, ctxs[k]->ev_trace, 0) != cudaSuccess) return fail(ctx, 2, "cross-device event wait failed");
+        const uint32_t j0 = (uint32_t)((uint64_t)p->height * g / n_ctx), j1 = (uint32_t)((uint64_t)p->height * (g + 1) / n_ctx);
+        // own buffer first: the local HBM read overlaps the first peer reads
+        const float *order[kMaxResolveBufs];
+        for (uint32_t k = 0; k < n_ctx; ++k) order[k] = bufs[(g + k) % n_ctx];
+        if (g == 0) CK(cudaEventRecord(c->ev[2], c->stream));
+        if (int rc = resolve_slab(c, order, n_ctx, p->width, p->height, j0, j1, spp_total, c->rgb8.p, c->stream)) { if (c != ctx) ctx->err = c->err; return rc; }
+        if (g == 0) CK(cudaEventRecord(c->ev[3], c->stream));
+        const size_t off = (size_t)(p->height - j1) * p->width * 3, bytes = (size_t)(j1 - j0) * p->width * 3;
+        if (bytes && cudaMemcpyAsync(rgb8_out + off, c->rgb8.p + off, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+            return fail(ctx, 2, "device-to-host copy failed on device %d", c->device);
+    }
+    unsigned long long nan_total = 0;
     for (uint32_t i = 0; i < n_ctx; ++i) {
         cudaSetDevice(ctxs[i]->device);
         if (cudaStreamSynchronize(ctxs[i]->stream) != cudaSuccess) return fail(ctx, 2, "device %d: kernel failed: %s", ctxs[i]->device, cudaGetErrorString(cudaGetLastError()));
+        unsigned long long nn = 0;
+        if (cudaMemcpy(&nn, ctxs[i]->stat_counters.p + ST_NAN_PIXELS, sizeof nn, cudaMemcpyDeviceToHost) == cudaSuccess) nan_total += nn;
     }
     CK(cudaSetDevice(ctx->device));
-    for (uint32_t i = 1; i < n_ctx; ++i) {
-        int can = 0;
-        CK(cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[i]->device));
-        if (!can) return fail(ctx, 3, "device %d cannot map device %d's memory (no peer access)", ctx->device, ctxs[i]->device);
-        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[i]->device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, 2, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
-        cudaGetLastError();
-    }
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (int rc = rtw_cuda_resolve_multi(ctx, bufs, n_ctx, p->width, p->height, spp_total, ctx->rgb8.p, ctx->stream)) return rc;
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    CK(cudaMemcpyAsync(rgb8_out, ctx->rgb8.p, npx * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->stats.ms_trace = ms;
     CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
     ctx->stats.ms_resolve = ms;
-    ctx->stats.n_launches = n_ctx + 1;
+    ctx->stats.n_launches = 2 * n_ctx;
+    ctx->stats.nan_pixels = nan_total;
+    ctx->stats.paths = (uint64_t)npx * spp;
+    ctx->stats.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return 0;
 }
 
@@ -1289,6 +1474,107 @@ int rtw_cuda_primary_hits(rtw_ctx *ctx, const rtw_camera *cam, uint32_t width, u
     if (ctx && !cam) return fail(ctx, 1, "camera is null");
     if (ctx && ((uint64_t)width * height > 0x7FFFFFFFull)) return fail(ctx, 1, "image too large");
     return probe_impl(ctx, width * height, nullptr, cam, width, height, precision, variant, prim_id, t, normal, nullptr);
+}
+
+// ---- unit probes of the stochastic device code (rtw_unit.cu) -------------------------------------------------------
+extern "C++" {
+namespace {
+template <class T>
+int to_device(rtw_ctx *ctx, DevBuf<T> &d, const T *h, size_t n) {
+    CK(d.alloc(n));
+    CK(cudaMemcpy(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+template <class T>
+int to_host(rtw_ctx *ctx, T *h, const DevBuf<T> &d, size_t n) {
+    CK(cudaMemcpy(h, d.p, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+}  // extern "C++"
+
+int rtw_cuda_unit_camera(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render_params *p, uint32_t n, const uint32_t *ijs, float *out) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!cam || !p || (n && (!ijs || !out))) return fail(ctx, 1, "null argument");
+    if (p->width == 0 || p->height == 0) return fail(ctx, 1, "empty image");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> d_in;
+    DevBuf<float> d_out;
+    int rc = to_device(ctx, d_in, ijs, (size_t)n * 3);
+    if (!rc && d_out.alloc((size_t)n * 14) != cudaSuccess) rc = fail(ctx, 2, "allocation failed");
+    if (!rc) {
+        cudaDeviceSynchronize();
+        const cudaError_t e = launch_unit_camera(lower_camera(cam), base_render(p), n, d_in.p, d_out.p, ctx->stream);
+        if (e != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, 2, "unit camera kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc) rc = to_host(ctx, out, d_out, (size_t)n * 14);
+    d_in.release(); d_out.release();
+    return rc;
+}
+
+int rtw_cuda_unit_samplers(rtw_ctx *ctx, uint32_t n, const float *u3, float *out) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (n && (!u3 || !out)) return fail(ctx, 1, "null argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<float> d_in, d_out;
+    int rc = to_device(ctx, d_in, u3, (size_t)n * 3);
+    if (!rc && d_out.alloc((size_t)n * 8) != cudaSuccess) rc = fail(ctx, 2, "allocation failed");
+    if (!rc) {
+        cudaDeviceSynchronize();
+        const cudaError_t e = launch_unit_samplers(n, d_in.p, d_out.p, ctx->stream);
+        if (e != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, 2, "unit samplers kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc) rc = to_host(ctx, out, d_out, (size_t)n * 8);
+    d_in.release(); d_out.release();
+    return rc;
+}
+
+int rtw_cuda_unit_uniforms(rtw_ctx *ctx, const rtw_render_params *p, uint32_t n, const uint32_t *psb, float *out) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!p || (n && (!psb || !out))) return fail(ctx, 1, "null argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> d_in;
+    DevBuf<float> d_out;
+    int rc = to_device(ctx, d_in, psb, (size_t)n * 3);
+    if (!rc && d_out.alloc((size_t)n * 8) != cudaSuccess) rc = fail(ctx, 2, "allocation failed");
+    if (!rc) {
+        cudaDeviceSynchronize();
+        const cudaError_t e = launch_unit_uniforms(base_render(p), n, d_in.p, d_out.p, ctx->stream);
+        if (e != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, 2, "unit uniforms kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc) rc = to_host(ctx, out, d_out, (size_t)n * 8);
+    d_in.release(); d_out.release();
+    return rc;
+}
+
+int rtw_cuda_unit_shade(rtw_ctx *ctx, const rtw_render_params *p, uint32_t n, const double *rays, const uint32_t *psb,
+                        uint32_t *prim_id, float *out) {
+    if (!ctx) return fail(nullptr, 1, "ctx is null");
+    if (!ctx->have_scene) return fail(ctx, 1, "no scene uploaded");
+    if (!p || (n && (!rays || !psb || !prim_id || !out))) return fail(ctx, 1, "null argument");
+    if (n == 0) return 0;
+    int variant = 0;
+    if (int rc = pick_variant(ctx, p->variant, &variant)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<float> fr((size_t)n * 7);
+    for (size_t k = 0; k < fr.size(); ++k) fr[k] = (float)rays[k];
+    DevBuf<float> d_rays, d_out;
+    DevBuf<uint32_t> d_psb, d_id;
+    int rc = to_device(ctx, d_rays, fr.data(), fr.size());
+    if (!rc) rc = to_device(ctx, d_psb, psb, (size_t)n * 3);
+    if (!rc && (d_out.alloc((size_t)n * 20) != cudaSuccess || d_id.alloc(n) != cudaSuccess)) rc = fail(ctx, 2, "allocation failed");
+    if (!rc) {
+        cudaDeviceSynchronize();
+        const cudaError_t e = launch_unit_shade(variant, ctx->scene, base_render(p), n, d_rays.p, d_psb.p, d_id.p, d_out.p, ctx->stream);
+        if (e != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, 2, "unit shade kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc) rc = to_host(ctx, out, d_out, (size_t)n * 20);
+    if (!rc) rc = to_host(ctx, prim_id, d_id, (size_t)n);
+    d_rays.release(); d_out.release(); d_psb.release(); d_id.release();
+    return rc;
 }
 
 int rtw_cuda_stats(rtw_ctx *ctx, rtw_stats *out) {

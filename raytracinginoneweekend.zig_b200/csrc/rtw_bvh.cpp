@@ -50,7 +50,7 @@ void box_to_f32(const Box3d &b, float out[6]) {
     for (int a = 0; a < 3; ++a) { out[a] = down(b.mn[a]); out[3 + a] = up(b.mx[a]); }
 }
 
-BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
+BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf, unsigned max_threads) {
     BvhResult out;
     const uint32_t n = (uint32_t)boxes.size();
     out.order.resize(n);
@@ -77,8 +77,7 @@ BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf) {
     unsigned n_threads = 1;
     constexpr uint32_t kSerialBelow = 8192;  // subtrees smaller than this are finished by the thread that reaches them
     if (n >= 4 * kSerialBelow) {
-        n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-        if (const char *e = getenv("RTW_BUILD_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
+        n_threads = max_threads ? max_threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
     }
     const uint32_t chunk_pairs = n_threads > 1 ? 512u : 1u;
     out.nodes.resize(2 * (size_t)n + 2 + (size_t)n_threads * 2 * chunk_pairs);

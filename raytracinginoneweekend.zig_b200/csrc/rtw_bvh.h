@@ -22,7 +22,8 @@ struct BvhResult {
 
 // Binned-SAH binary BVH over `boxes` (one per primitive, reference order).  Leaves hold at most
 // `max_leaf` primitives.  Node boxes are fp32, rounded outward from the f64 boxes.
-BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf = 4);
+// max_threads = 0: as many as the machine offers (capped at 16)
+BvhResult build_bvh(const std::vector<Box3d> &boxes, uint32_t max_leaf = 4, unsigned max_threads = 0);
 
 // The f64 box rounded outward to fp32: out = (min xyz, max xyz).
 void box_to_f32(const Box3d &b, float out[6]);

@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
 // K4 resolve: out = 256 * clamp(sqrt(sum / spp), 0, 0.999) truncated to u8, written to row H-1-j.
 // Sums up to kMaxResolveBufs accumulation buffers first; with peer access enabled those may live on
 // other GPUs, i.e. the cross-GPU reduction and the resolve are one kernel over NVLink peer memory.
+// Works on the scanline slab [row_begin, row_end): in the multi-GPU render every GPU resolves its own slab
+// from all N buffers (reduce-scatter shaped: each GPU ingests (N-1)/N of ONE buffer over NVLink).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t quantise(float sum, float scale, unsigned int &nan_flag) {
     float c = sqrtf(sum * scale);
@@ -304,8 +306,8 @@ __device__ __forceinline__ uint32_t quantise(float sum, float scale, unsigned in
 }
 
 __global__ void __launch_bounds__(256) k_resolve(ResolveArgs a) {
-    const uint32_t n = a.width * a.height;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = a.row_end * a.width;
+    const uint32_t idx = a.row_begin * a.width + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int nan_flag = 0u;
     if (idx < n) {
         float4 s = __ldcs(a.bufs[0] + idx);
@@ -328,8 +330,8 @@ __global__ void __launch_bounds__(256) k_resolve(ResolveArgs a) {
 // Same, four pixels per thread when the width is a multiple of four: 4 x 16-byte loads per buffer, one
 // 12-byte (3 x u32) store — the byte-wise stores of k_resolve reach only ~1.2 TB/s.
 __global__ void __launch_bounds__(256) k_resolve4(ResolveArgs a) {
-    const uint32_t n4 = (a.width * a.height) >> 2;
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n4 = (a.row_end * a.width) >> 2;
+    const uint32_t q = ((a.row_begin * a.width) >> 2) + blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int nan_flag = 0u;
     if (q < n4) {
         const uint32_t idx = q << 2;
@@ -410,6 +412,16 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     }
 }
 
+// max_depth == 0: rayColor returns black before intersecting (main.zig:105-108); only the sample count moves
+__global__ void __launch_bounds__(256) k_add_samples(float4 *accum, uint32_t n, float count) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) accum[idx].w += count;
+}
+cudaError_t launch_add_samples(float4 *accum, uint32_t n_pixels, float count, cudaStream_t st) {
+    k_add_samples<<<(n_pixels + 255) / 256, 256, 0, st>>>(accum, n_pixels, count);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP32 peak: 8 independent FFMA chains per thread, 2 flops per FFMA.
 // ---------------------------------------------------------------------------------------------
@@ -480,7 +492,8 @@ int megakernel_ctas_per_sm(int variant, bool stats, bool pooled, const DevScene 
 }
 
 cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st) {
-    const uint32_t n = a.width * a.height;
+    const uint32_t n = a.width * (a.row_end - a.row_begin);  // rows [row_begin, row_end) of the accumulation buffers
+    if (n == 0) return cudaSuccess;
     // 4-pixel path needs rows that are multiples of 4 pixels (12-byte groups stay 4-byte aligned) and an aligned base
     if ((a.width & 3u) == 0 && (reinterpret_cast<uintptr_t>(a.rgb8) & 3u) == 0) k_resolve4<<<((n >> 2) + 255) / 256, 256, 0, st>>>(a);
     else k_resolve<<<(n + 255) / 256, 256, 0, st>>>(a);

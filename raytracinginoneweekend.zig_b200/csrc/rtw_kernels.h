@@ -14,6 +14,7 @@ struct ResolveArgs {
     const float4 *bufs[kMaxResolveBufs];
     uint32_t n_bufs;
     uint32_t width, height;
+    uint32_t row_begin, row_end;  // reference scanlines j (bottom row = 0) this launch resolves
     float scale;  // 1 / spp_total
     uint8_t *rgb8;
     unsigned long long *nan_counter;  // may be null
@@ -27,6 +28,14 @@ cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st);
 cudaError_t launch_probe(int variant, const DevScene &sc, uint32_t n, const float *rays, uint32_t *prim_id, float *t,
                          float *normal, float *uv, cudaStream_t st);
 cudaError_t launch_ffma_peak(float *out, int grid, int iters, cudaStream_t st);
+cudaError_t launch_add_samples(float4 *accum, uint32_t n_pixels, float count, cudaStream_t st);
+
+// rtw_unit.cu (unit-level probes of the production stochastic code: parity instruments)
+cudaError_t launch_unit_camera(const DevCamera &cam, const DevRender &rp, uint32_t n, const uint32_t *ijs, float *out, cudaStream_t st);
+cudaError_t launch_unit_samplers(uint32_t n, const float *u3, float *out, cudaStream_t st);
+cudaError_t launch_unit_uniforms(const DevRender &rp, uint32_t n, const uint32_t *psb, float *out, cudaStream_t st);
+cudaError_t launch_unit_shade(int variant, const DevScene &sc, const DevRender &rp, uint32_t n, const float *rays, const uint32_t *psb,
+                              uint32_t *prim_id, float *out, cudaStream_t st);
 
 // rtw_wavefront.cu (K2: wavefront schedule of the same path)
 struct WfCounters {

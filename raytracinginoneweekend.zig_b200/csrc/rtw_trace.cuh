@@ -656,14 +656,21 @@ __device__ __forceinline__ float2 sample_unit_disk(float u1, float u2) {  // ran
     return make_float2(rad * cs, rad * sn);
 }
 
-// Camera.getRay main.zig:91-100 + the (u,v) jitter of main.zig:390-391.  One Philox block: five
-// 24-bit uniforms sliced out of its 128 bits.
+// The five uniforms of one camera ray — pixel jitter (ju, jv), lens disk (l1, l2), shutter time (tm) — sliced out of
+// the 128 bits of ONE Philox block: four 24-bit values from the high bits of the four words, the fifth from the low
+// bytes of the first three (disjoint bits, so the five are independent).
+__device__ __forceinline__ void camera_uniforms(const DevRender &rp, uint32_t pixel, uint32_t sample, float (&u)[5]) {
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.philox_keys);
+    u[0] = u01_24(rn.x); u[1] = u01_24(rn.y); u[2] = u01_24(rn.z); u[3] = u01_24(rn.w);
+    u[4] = u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8));
+}
+
+// Camera.getRay main.zig:91-100 + the (u,v) jitter of main.zig:390-391.
 __device__ __forceinline__ Ray camera_ray(const DevCamera &cam, const DevRender &rp, uint32_t pixel, uint32_t i,
                                           uint32_t j, uint32_t sample) {
-    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.philox_keys);
-    const float ju = u01_24(rn.x), jv = u01_24(rn.y);
-    const float l1 = u01_24(rn.z), l2 = u01_24(rn.w);
-    const float tm = u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8));
+    float un[5];
+    camera_uniforms(rp, pixel, sample, un);
+    const float ju = un[0], jv = un[1], l1 = un[2], l2 = un[3], tm = un[4];
     const float s = ((float)i + ju) * rp.inv_wm1;  // main.zig:390-391 (division by W-1 as a multiply)
     const float t = ((float)j + jv) * rp.inv_hm1;
     const float2 dk = sample_unit_disk(l1, l2);

@@ -52,6 +52,12 @@ def load(build_if_missing=True):
                                         u32p, dp, dp]
     L.rtw_cuda_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     L.rtw_cuda_measure_fp32_peak.argtypes = [vp, dp, dp]
+    L.rtw_cuda_unit_camera.argtypes = [vp, C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), C.c_uint32, u32p, fp]
+    L.rtw_cuda_unit_samplers.argtypes = [vp, C.c_uint32, fp, fp]
+    L.rtw_cuda_unit_uniforms.argtypes = [vp, C.POINTER(abi.RenderParams), C.c_uint32, u32p, fp]
+    L.rtw_cuda_unit_shade.argtypes = [vp, C.POINTER(abi.RenderParams), C.c_uint32, dp, u32p, u32p, fp]
+    L.rtw_cuda_create_multi.argtypes = [C.c_uint32, C.POINTER(vp)]
+    L.rtw_cuda_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     for name in abi.CUDA_SYMBOLS:
         getattr(L, name)  # AttributeError here = the .so does not export what the header declares
     _lib = L
@@ -73,17 +79,47 @@ def render_multi(contexts, cam, params, rgb8=None):
     return rgb8
 
 
+def create_multi(n_gpus):
+    """rtw_cuda_create_multi: contexts on devices 0..n_gpus-1 with all-pairs peer access already enabled."""
+    L = load()
+    arr = (C.c_void_p * n_gpus)()
+    rc = L.rtw_cuda_create_multi(n_gpus, arr)
+    if rc != 0:
+        raise RtwCudaError(f"rtw_cuda_create_multi({n_gpus}) -> {rc}: {L.rtw_cuda_last_error(None).decode()}")
+    return [Context(device=i, handle=arr[i]) for i in range(n_gpus)]
+
+
 class Context:
     """One rtw_ctx: a CUDA device + an uploaded scene."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
         self.L = load()
-        self.h = C.c_void_p()
-        rc = self.L.rtw_cuda_create(device, C.byref(self.h))
-        if rc != 0:
-            raise RtwCudaError(f"rtw_cuda_create({device}) -> {rc}: {self.L.rtw_cuda_last_error(None).decode()}")
+        self.h = C.c_void_p(handle) if handle else C.c_void_p()
+        if not handle:
+            rc = self.L.rtw_cuda_create(device, C.byref(self.h))
+            if rc != 0:
+                raise RtwCudaError(f"rtw_cuda_create({device}) -> {rc}: {self.L.rtw_cuda_last_error(None).decode()}")
         self.device = device
         self._keep = None
+
+    def set_option(self, name, value):
+        """Tuning knob (same names as the environment variables, e.g. RTW_BVH_BUILDER); value None = built-in default."""
+        v = None if value is None else str(value).encode()
+        self._check(self.L.rtw_cuda_set_option(self.h, name.encode(), v), "rtw_cuda_set_option")
+
+    def options(self, **kw):
+        """with ctx.options(RTW_BVH_BUILDER="lbvh"): ...   — set, then restore the defaults"""
+        ctx = self
+
+        class _Scope:
+            def __enter__(self_inner):
+                for k, v in kw.items():
+                    ctx.set_option(k, v)
+
+            def __exit__(self_inner, *exc):
+                for k in kw:
+                    ctx.set_option(k, None)
+        return _Scope()
 
     def close(self):
         if getattr(self, "h", None):
@@ -153,6 +189,44 @@ class Context:
                                                  ids.ctypes.data_as(C.POINTER(C.c_uint32)), _dp(t), _dp(nrm)),
                     "rtw_cuda_primary_hits")
         return ids, t, nrm
+
+    # ---- unit probes of the stochastic device code (parity instruments) ----
+    def unit_camera(self, cam, params, ijs):
+        """ijs[n,3] = (i, j, sample) -> float32[n,14]: ray(7) | uniforms ju jv l1 l2 tm | disk point(2)"""
+        ijs = np.ascontiguousarray(ijs, dtype=np.uint32).reshape(-1, 3)
+        out = np.zeros((ijs.shape[0], 14), dtype=np.float32)
+        self._check(self.L.rtw_cuda_unit_camera(self.h, C.byref(cam), C.byref(params), ijs.shape[0],
+                                                ijs.ctypes.data_as(C.POINTER(C.c_uint32)), out.ctypes.data_as(C.POINTER(C.c_float))),
+                    "rtw_cuda_unit_camera")
+        return out
+
+    def unit_samplers(self, u3):
+        """u3[n,3] uniforms -> float32[n,8]: unit vector(3) | ball point(3) | disk point(2)"""
+        u3 = np.ascontiguousarray(u3, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((u3.shape[0], 8), dtype=np.float32)
+        self._check(self.L.rtw_cuda_unit_samplers(self.h, u3.shape[0], u3.ctypes.data_as(C.POINTER(C.c_float)),
+                                                  out.ctypes.data_as(C.POINTER(C.c_float))), "rtw_cuda_unit_samplers")
+        return out
+
+    def unit_uniforms(self, params, psb):
+        """psb[n,3] = (pixel, sample, block) -> (float32[n,4] uniforms, uint32[n,4] raw Philox words)"""
+        psb = np.ascontiguousarray(psb, dtype=np.uint32).reshape(-1, 3)
+        out = np.zeros((psb.shape[0], 8), dtype=np.float32)
+        self._check(self.L.rtw_cuda_unit_uniforms(self.h, C.byref(params), psb.shape[0], psb.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  out.ctypes.data_as(C.POINTER(C.c_float))), "rtw_cuda_unit_uniforms")
+        return out[:, :4].copy(), out[:, 4:].copy().view(np.uint32)
+
+    def unit_shade(self, params, rays, psb):
+        """rays[n,7], psb[n,3] = (pixel, sample, bounce) -> (prim_id[n], float32[n,20]); layout in include/rtw_cuda.h"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        psb = np.ascontiguousarray(psb, dtype=np.uint32).reshape(-1, 3)
+        n = rays.shape[0]
+        ids = np.zeros(n, dtype=np.uint32)
+        out = np.zeros((n, 20), dtype=np.float32)
+        self._check(self.L.rtw_cuda_unit_shade(self.h, C.byref(params), n, _dp(rays), psb.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                               ids.ctypes.data_as(C.POINTER(C.c_uint32)), out.ctypes.data_as(C.POINTER(C.c_float))),
+                    "rtw_cuda_unit_shade")
+        return ids, out
 
     def stats(self):
         s = abi.Stats()

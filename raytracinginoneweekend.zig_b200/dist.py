@@ -17,13 +17,18 @@ def spp_range(rank, world, spp_total, spp_begin=0):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def render_distributed(accumulate, resolve, accum, spp_total, rank, world, group=None, reduce_op=None):
+def render_distributed(accumulate, resolve, accum, spp_total, rank, world, group=None, reduce_op=None,
+                       after_accumulate=None):
     """accumulate(lo, hi) adds this rank's samples into `accum` (a torch tensor, H x W x 4 fp32);
     then the buffers are summed onto rank 0, which calls resolve(accum) and returns its result.
-    `accumulate`/`resolve` are callables so the same control flow runs on CPU tensors under gloo in tests."""
+    `accumulate`/`resolve` are callables so the same control flow runs on CPU tensors under gloo in tests and on
+    device pointers under NCCL in bench.py; `after_accumulate` (optional) is called between the two phases (bench.py
+    records a CUDA event there to time the path-tracing kernel on its own)."""
     import torch.distributed as dist
     lo, hi = spp_range(rank, world, spp_total)
     accumulate(lo, hi)
+    if after_accumulate is not None:
+        after_accumulate()
     if world > 1:
         dist.reduce(accum, dst=0, op=reduce_op or dist.ReduceOp.SUM, group=group)
     if rank == 0:

@@ -3,7 +3,7 @@
 //! Field order and types mirror the header one for one; tests/test_abi.py pins the C side.
 const std = @import("std");
 
-pub const ABI_VERSION: u32 = 2;
+pub const ABI_VERSION: u32 = 3;
 pub const MISS: u32 = 0xFFFFFFFF;
 
 pub const PrimKind = enum(u32) { sphere = 0, moving_sphere = 1, xy_rect = 2, xz_rect = 3, yz_rect = 4 };
@@ -93,9 +93,12 @@ pub const Stats = extern struct {
     ms_bvh_build: f64,
     bvh_builder: u32, // 0 = host binned SAH, 1 = device Morton/radix tree
     reserved0: u32,
+    ms_wall: f64, // host wall clock of the last render / render_multi call
 };
 pub extern "c" fn rtw_cuda_stats(ctx: *Ctx, out: *Stats) c_int;
 
+pub extern "c" fn rtw_cuda_create_multi(n_gpus: u32, out: [*]?*Ctx) c_int;
+pub extern "c" fn rtw_cuda_set_option(ctx: *Ctx, name: [*:0]const u8, value: ?[*:0]const u8) c_int;
 pub extern "c" fn rtw_cuda_render_multi(ctxs: [*]const ?*Ctx, n_ctx: u32, cam: *const Camera, params: *const RenderParams, rgb8_out: [*]u8) c_int;
 
 pub const Error = error{ CudaUnavailable, SceneRejected, RenderFailed };

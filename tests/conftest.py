@@ -39,3 +39,20 @@ def ctx(rtw):
     c = rtw.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture
+def knobs(ctx):
+    """Tuning knobs of the session context (rtw_cuda_set_option; the library reads the environment only once, at
+    rtw_cuda_create).  knobs.setenv(name, value) mirrors monkeypatch.setenv; everything is restored afterwards."""
+    touched = []
+
+    class K:
+        @staticmethod
+        def setenv(name, value):
+            ctx.set_option(name, value)
+            touched.append(name)
+
+    yield K
+    for name in touched:
+        ctx.set_option(name, None)

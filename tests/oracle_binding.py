@@ -24,6 +24,47 @@ def build(force=False):
     return LIB_PATH
 
 
+NATIVE_LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle_native.so")
+
+
+def _cpu_stamp():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()[:16]
+    except OSError:
+        pass
+    return "unknown"
+
+
+def use_native_build():
+    """Switch this process to the TIMING build of the oracle (-O3 -march=native, contraction allowed), compiling it on
+    this machine if it was not compiled here before.  Must be called before the first lib().  Returns a description of
+    what will be loaded.  Parity tests never call this: they use the portable -ffp-contract=off build."""
+    global LIB_PATH
+    assert _lib is None, "use_native_build() must come before the library is loaded"
+    stamp_path = NATIVE_LIB_PATH + ".cpu"
+    stamp = _cpu_stamp()
+    try:
+        have = os.path.exists(NATIVE_LIB_PATH) and open(stamp_path).read() == stamp
+    except OSError:
+        have = False
+    if not have:
+        try:
+            if os.path.exists(NATIVE_LIB_PATH):
+                os.remove(NATIVE_LIB_PATH)
+            subprocess.run(["make", "-C", ORACLE_DIR, "native"], check=True, capture_output=True, timeout=300)
+            with open(stamp_path, "w") as f:
+                f.write(stamp)
+            have = True
+        except Exception as e:  # no compiler on this host: time the portable build and say so
+            return f"built g++ -O3 -ffp-contract=off (portable parity build; native build failed: {type(e).__name__})"
+    LIB_PATH = NATIVE_LIB_PATH
+    return "built on this host with g++ -O3 -march=native (FMA contraction allowed)"
+
+
 def _abi():
     import rtw_b200
     return rtw_b200.abi
@@ -36,7 +77,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    build()
+    if LIB_PATH != NATIVE_LIB_PATH:
+        build()
     abi = _abi()
     L = C.CDLL(LIB_PATH)
     dp, u32p, u64p, u8p = (C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),

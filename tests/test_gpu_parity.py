@@ -56,6 +56,14 @@ def test_production_primary_hits_vs_f64_oracle(rtw, oracle, ctx, sid, grid, W, H
         gid, gt, gn = ctx.primary_hits(cam, W, H, 0, variant)
         mism = gid != oid
         assert mism.mean() <= 5e-4, f"{mism.sum()} of {oid.size} ids differ from the f64 oracle"
+        # ... and every one of them sits on a silhouette / seam: 8-adjacent to a pixel where the ORACLE's id map changes,
+        # and what the device saw there is the id of one of the oracle's neighbouring pixels (fp32 moved an edge by less
+        # than a pixel; it did not invent or lose a surface)
+        pad = np.pad(oid, 1, mode="edge")
+        neigh = np.stack([pad[1 + dy:1 + dy + H, 1 + dx:1 + dx + W] for dy in (-1, 0, 1) for dx in (-1, 0, 1)])
+        on_edge = (neigh != oid[None]).any(axis=0)
+        assert on_edge[mism].all(), f"{(mism & ~on_edge).sum()} mismatching pixels are not on an id edge of the oracle map"
+        assert (neigh == gid[None]).any(axis=0)[mism].all(), "a mismatching pixel shows an id none of its oracle neighbours has"
         ok = ~mism & (oid != MISS)
         assert (np.abs(gt - ot)[ok] <= 2e-3 * np.maximum(1.0, np.abs(ot[ok]))).all()
         assert np.abs(gn - on)[ok].max() <= 2e-3
@@ -103,10 +111,10 @@ def test_trace_rays_random_scene(rtw, oracle, ctx, seed):
 
 
 @pytest.mark.parametrize("builder", ["sah", "lbvh"])
-def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx, monkeypatch, builder):
+def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx, knobs, builder):
     """10^4-sphere field (config C4's generator at grid 50): device BVH == device linear scan == oracle, for the
     host (binned SAH) and the device (Morton / radix tree) builder."""
-    monkeypatch.setenv("RTW_BVH_BUILDER", builder)
+    knobs.setenv("RTW_BVH_BUILDER", builder)
     hs = rtw.HostScene(rtw.host_lib.SCENE_SPHERE_FIELD, grid=50)
     osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
     ctx.upload_scene(hs.desc, keep=hs)
@@ -127,10 +135,10 @@ def test_bvh_equals_linear_scan_many_prims(rtw, oracle, ctx, monkeypatch, builde
 
 
 @pytest.mark.parametrize("seed", [5, 6])
-def test_device_built_bvh_mixed_scene(rtw, oracle, ctx, monkeypatch, seed):
+def test_device_built_bvh_mixed_scene(rtw, oracle, ctx, knobs, seed):
     """Device builder on a mixed scene (rects, instanced boxes, moving and instanced spheres, a ground sphere that
     dwarfs the rest and is grafted next to the root): reference-order probe through the BVH == linear scan == oracle."""
-    monkeypatch.setenv("RTW_BVH_BUILDER", "lbvh")
+    knobs.setenv("RTW_BVH_BUILDER", "lbvh")
     rng = np.random.default_rng(seed)
     desc = scene_util.random_scene(rng, n_spheres=400, n_moving=200, n_rects=60, n_boxes=8, n_inst_spheres=20)
     osc = oracle.OracleScene.from_desc(desc, keep=desc)
@@ -149,16 +157,16 @@ def test_device_built_bvh_mixed_scene(rtw, oracle, ctx, monkeypatch, seed):
     hs_cam = rtw.camera_init((26, 6, 8), (0, 0, 0), (0, 1, 0), 40.0, 1.5, 0.0, 10.0, 0.0, 1.0)
     p = ctx.params(96, 64, 0, 8, 8, 20, rtw.abi.VARIANT_MEGA_BVH, rtw.abi.FLAG_DETERMINISTIC, 7, (0.7, 0.8, 1.0))
     _, acc_l = ctx.render(hs_cam, p, want_accum=True)
-    monkeypatch.setenv("RTW_BVH_BUILDER", "sah")
+    knobs.setenv("RTW_BVH_BUILDER", "sah")
     ctx.upload_scene(desc, keep=desc)
     assert ctx.stats()["bvh_builder"] == rtw.abi.BVH_BUILDER_SAH
     _, acc_s = ctx.render(hs_cam, p, want_accum=True)
     assert np.array_equal(acc_l, acc_s)
 
 
-def test_device_built_bvh_coincident_centroids(rtw, oracle, ctx, monkeypatch):
+def test_device_built_bvh_coincident_centroids(rtw, oracle, ctx, knobs):
     """Equal Morton keys (stacks of concentric spheres): the radix tree splits ties by position and stays shallow."""
-    monkeypatch.setenv("RTW_BVH_BUILDER", "lbvh")
+    knobs.setenv("RTW_BVH_BUILDER", "lbvh")
     b = scene_util.DescBuilder()
     m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
     for k in range(300):
@@ -261,6 +269,109 @@ def test_validation_errors(rtw, ctx):
     with pytest.raises(rtw.RtwCudaError, match="no scene uploaded"):
         c2.render(cam, ctx.params(8, 8, 0, 1, 1))
     c2.close()
+    # the wavefront packs (sample, bounce) into 26 + 6 bits: parameters beyond that are refused, not mis-rendered
+    with pytest.raises(rtw.RtwCudaError, match="max_depth <= 63"):
+        ctx.render(cam, ctx.params(8, 8, 0, 1, 1, 64, rtw.abi.VARIANT_WAVEFRONT))
+    ctx.render(cam, ctx.params(8, 8, 0, 1, 1, 63, rtw.abi.VARIANT_WAVEFRONT))
+    with pytest.raises(rtw.RtwCudaError, match="unknown option"):
+        ctx.set_option("RTW_NO_SUCH_KNOB", "1")
+    # tables with a count but no pointer
+    for field in ("materials", "textures"):
+        b2 = scene_util.DescBuilder()
+        b2.sphere((0, 0, 0), 1, b2.diffuse(b2.solid((0.5, 0.5, 0.5))))
+        d2 = b2.build()
+        setattr(d2, field, None)
+        with pytest.raises(rtw.RtwCudaError, match=f"{field} is null"):
+            ctx.upload_scene(d2)
+    # checker graphs: a cycle, and nesting deeper than the device follows
+    b3 = scene_util.DescBuilder()
+    t0 = b3.checker((0, 0, 0), (1, 1, 1))
+    b3.sphere((0, 0, 0), 1, b3.diffuse(t0))
+    d3 = b3.build()
+    d3.textures[t0].a = t0
+    with pytest.raises(rtw.RtwCudaError, match="checker nesting"):
+        ctx.upload_scene(d3)
+    b4 = scene_util.DescBuilder()
+    t = b4.solid((0.1, 0.2, 0.3))
+    for _ in range(9):
+        b4.texs.append(rtw.abi.Texture(kind=rtw.abi.TEX_CHECKER, a=t, b=t))
+        t = len(b4.texs) - 1
+    b4.sphere((0, 0, 0), 1, b4.diffuse(t))
+    with pytest.raises(rtw.RtwCudaError, match="checker nesting"):
+        ctx.upload_scene(b4.build())
+
+
+def test_depth_zero_is_black(rtw, oracle, ctx):
+    """rayColor returns (0,0,0) before intersecting anything when depth == 0 (main.zig:105-108): the frame is black and
+    every sample is counted — all variants, including the sky pixels (no background either)."""
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
+    assert (osc.ray_color([13, 2, 3, -13, -2, -3, 0.5], hs.background, 0, 1)["color"] == 0).all()
+    for variant in (1, 2, 3):
+        for flags in (0, rtw.abi.FLAG_DETERMINISTIC):
+            rgb, acc = ctx.render(hs.camera(), ctx.params(40, 24, 0, 6, 6, 0, variant, flags, 42, hs.background), want_accum=True)
+            assert (rgb == 0).all() and (acc[..., :3] == 0).all() and (acc[..., 3] == 6).all()
+
+
+def test_negative_radius_sphere(rtw, oracle, ctx):
+    """The hollow-glass idiom: a sphere of radius -0.9 inside one of radius 1 (Sphere.hit uses r*r and divides by r,
+    hittable.zig:99,120: the inner normal flips).  Its boudingBox would be inverted; the library boxes |r|."""
+    b = scene_util.DescBuilder()
+    glass = b.glass(1.5)
+    grey = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    b.sphere((0, -1001, 0), 1000.0, grey)
+    b.sphere((0, 0, 0), 1.0, glass)
+    b.sphere((0, 0, 0), -0.9, glass)
+    b.moving_sphere((2.5, 0, 0), (2.5, 0.3, 0), 0.0, 1.0, -0.5, glass)
+    for k in range(70):  # enough primitives for a real tree
+        b.sphere((np.cos(k) * 4, -0.8, np.sin(k) * 4), 0.2, grey)
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    rng = np.random.default_rng(4)
+    rays = scene_util.random_rays(rng, 30000, extent=1.5)
+    for precision in (32, 64):
+        oid, ot, on, _ = osc.trace_rays(rays, precision)
+        assert (oid == 2).sum() > 500 and (oid == 3).sum() > 100
+        for variant in (1, 2):
+            gid, gt, gn, _ = ctx.trace_rays(rays, precision, variant)
+            assert np.array_equal(gid, oid) and np.array_equal(gt, ot) and np.array_equal(gn, on)
+    oid, ot, on, _ = osc.trace_rays(rays, 64)
+    for variant in (1, 2):
+        gid, gt, gn, _ = ctx.trace_rays(rays, 0, variant)
+        ok = gid == oid
+        assert ok.mean() > 0.999
+        hit = ok & (oid != MISS)
+        assert np.abs(gn - on)[hit].max() < 2e-3  # the flipped inner normal included
+
+
+def test_accumulate_calls_on_two_streams_do_not_race(rtw, ctx):
+    """One work queue per context: two rtw_cuda_accumulate calls of one context issued on different streams are ordered
+    on the device by the library.  The sum of both equals the two sample ranges rendered one after the other."""
+    import torch
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    W, H = 256, 144
+    cam = hs.camera(aspect=W / H)
+    det = rtw.abi.FLAG_DETERMINISTIC
+    pa = ctx.params(W, H, 0, 24, 48, 50, 0, det, 42, hs.background)
+    pb = ctx.params(W, H, 24, 48, 48, 50, 0, det, 42, hs.background)
+    seq_a, seq_b = torch.zeros(H, W, 4, device="cuda"), torch.zeros(H, W, 4, device="cuda")
+    ctx.accumulate(cam, pa, seq_a.data_ptr(), None)
+    torch.cuda.synchronize()
+    ctx.accumulate(cam, pb, seq_b.data_ptr(), None)
+    torch.cuda.synchronize()
+    par_a, par_b = torch.zeros_like(seq_a), torch.zeros_like(seq_b)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        par_a.zero_(); par_b.zero_()
+        torch.cuda.synchronize()
+        ctx.accumulate(cam, pa, par_a.data_ptr(), s1.cuda_stream)
+        ctx.accumulate(cam, pb, par_b.data_ptr(), s2.cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(par_a, seq_a) and torch.equal(par_b, seq_b)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -358,10 +469,10 @@ def test_image_parity(rtw, oracle, ctx, sid, grid, W, H, spp, variant):
     assert psnr > 10.0
 
 
-def test_flat_and_bvh_render_the_same_paths(rtw, ctx, monkeypatch):
+def test_flat_and_bvh_render_the_same_paths(rtw, ctx, knobs):
     """Identical Philox keys + identical closest hits => identical per-sample radiance; with one chunk the
     summation order is fixed too, so the two traversal variants must agree bit for bit."""
-    monkeypatch.setenv("RTW_SPP_CHUNK", "0")
+    knobs.setenv("RTW_SPP_CHUNK", "0")
     hs = rtw.HostScene(1, grid=11)
     ctx.upload_scene(hs.desc, keep=hs)
     cam = hs.camera()
@@ -372,7 +483,7 @@ def test_flat_and_bvh_render_the_same_paths(rtw, ctx, monkeypatch):
     assert not np.array_equal(a, c)  # a different seed gives different samples
 
 
-def test_spp_split_equals_full_render(rtw, ctx, monkeypatch):
+def test_spp_split_equals_full_render(rtw, ctx, knobs):
     """The multi-GPU partition: sample ranges rendered separately and summed == the full range
     (Philox is keyed by the absolute sample index).  Only fp32 summation order differs."""
     import torch
@@ -395,7 +506,7 @@ def test_spp_split_equals_full_render(rtw, ctx, monkeypatch):
     diff = np.abs(out.cpu().numpy().astype(int) - full[0].astype(int))
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
     # chunked (atomic) and unchunked accumulation agree to fp32 rounding
-    monkeypatch.setenv("RTW_SPP_CHUNK", "5")
+    knobs.setenv("RTW_SPP_CHUNK", "5")
     chunked = ctx.render(cam, ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, hs.background), want_accum=True)
     np.testing.assert_allclose(chunked[1][..., :3], full[1][..., :3], rtol=2e-5, atol=1e-5)
     assert (chunked[1][..., 3] == spp).all()
@@ -436,11 +547,11 @@ def test_white_furnace_on_device(rtw, ctx):
 
 
 @pytest.mark.parametrize("sid,grid,W,H,spp", [(1, 3, 200, 120, 33), (6, 3, 97, 61, 40), (1, 11, 160, 90, 16), (7, 3, 120, 68, 24)])
-def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, monkeypatch, sid, grid, W, H, spp):
+def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, knobs, sid, grid, W, H, spp):
     """K2 (generate / extend / shade+compact) is a different schedule of the same path: identical Philox keys and
     identical closest hits => identical per-sample radiance; only fp32 summation order differs.  Ragged frame
     sizes and a small slot count force many refill iterations."""
-    monkeypatch.setenv("RTW_WF_SLOTS", "8192")
+    knobs.setenv("RTW_WF_SLOTS", "8192")
     hs = rtw.HostScene(sid, grid=grid)
     ctx.upload_scene(hs.desc, keep=hs)
     cam = hs.camera(aspect=W / H)
@@ -459,30 +570,45 @@ def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, monkeypatc
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
-def test_render_multi_sums_peer_buffers_in_the_resolve_kernel(rtw, ctx):
-    """Single-process multi-GPU: each device traces its sample range, device 0's resolve kernel reads the other
-    devices' buffers over NVLink peer mappings.  Must equal the 1-GPU render of the same sample set."""
+def test_render_multi_slab_resolve_on_one_device(rtw, ctx):
+    """rtw_cuda_render_multi with a single context runs the same slab-resolve code path as N devices (one slab = the
+    whole image, no peers): byte-identical to rtw_cuda_render, for widths that take the 4-pixel and the 1-pixel kernel."""
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    for W, H, spp in ((320, 180, 9), (101, 67, 5)):
+        cam = hs.camera(aspect=W / H)
+        p = ctx.params(W, H, 0, spp, spp, 50, 0, rtw.abi.FLAG_DETERMINISTIC, 42, hs.background)
+        one = ctx.render(cam, p)[0]
+        multi = rtw.render_multi([ctx], cam, p)
+        assert np.array_equal(one, multi)
+        assert ctx.stats()["ms_wall"] > 0
+
+
+def test_render_multi_slab_parallel_resolve_over_peers(rtw, ctx):
+    """Single-process multi-GPU: each device traces its sample range, then every device resolves one scanline slab from
+    all buffers over NVLink peer mappings and copies its rows to the host.  Must equal the 1-GPU render of the same
+    sample set.  (bench.py --gpus N asserts the same inside the driver's multi-GPU run.)"""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     n = min(n, 4)
     hs = rtw.HostScene(1)
-    W, H, spp = 320, 180, 37
-    cam = hs.camera(aspect=W / H)
     ctx.upload_scene(hs.desc, keep=hs)
-    p = ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, hs.background)
-    one = ctx.render(cam, p)[0]
-    others = [rtw.Context(i) for i in range(1, n)]
+    group = rtw.create_multi(n)
     try:
-        for c in others:
+        for c in group:
             c.upload_scene(hs.desc, keep=hs)
-        multi = rtw.render_multi([ctx] + others, cam, p)
+        for W, H, spp in ((320, 180, 37), (322, 181, 10)):  # 181 rows over 4 devices: ragged slabs; 322: the 1-pixel kernel
+            cam = hs.camera(aspect=W / H)
+            p = ctx.params(W, H, 0, spp, spp, 50, 0, 0, 42, hs.background)
+            one = ctx.render(cam, p)[0]
+            multi = rtw.render_multi(group, cam, p)
+            diff = np.abs(multi.astype(int) - one.astype(int))
+            assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
     finally:
-        for c in others:
+        for c in group:
             c.close()
-    diff = np.abs(multi.astype(int) - one.astype(int))
-    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
 def test_instanced_spheres_uv_and_image(rtw, oracle, ctx, earth_rgba):

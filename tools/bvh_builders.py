@@ -16,10 +16,10 @@ ctx = rtw_b200.Context(0)
 hs = rtw_b200.HostScene(scene, grid=grid)
 cam = hs.camera(aspect=W / H)
 accum = torch.zeros(H, W, 4, device="cuda")
-os.environ["RTW_UPLOAD_TRACE"] = "1"
+ctx.set_option("RTW_UPLOAD_TRACE", "1")
 for builder, leaf_max in (("sah", 4), ("lbvh", 4), ("lbvh", 2), ("lbvh", 1)):
-    os.environ["RTW_BVH_BUILDER"] = builder
-    os.environ["RTW_BVH_LEAF_MAX"] = str(leaf_max)
+    ctx.set_option("RTW_BVH_BUILDER", builder)
+    ctx.set_option("RTW_BVH_LEAF_MAX", leaf_max)
     ctx.upload_scene(hs.desc, keep=hs)
     up = ctx.stats()
     p = ctx.params(W, H, 0, spp, spp, 50, abi.VARIANT_MEGA_BVH, 0, 42, hs.background)
