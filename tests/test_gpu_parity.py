@@ -56,14 +56,21 @@ def test_production_primary_hits_vs_f64_oracle(rtw, oracle, ctx, sid, grid, W, H
         gid, gt, gn = ctx.primary_hits(cam, W, H, 0, variant)
         mism = gid != oid
         assert mism.mean() <= 5e-4, f"{mism.sum()} of {oid.size} ids differ from the f64 oracle"
-        # ... and every one of them sits on a silhouette / seam: 8-adjacent to a pixel where the ORACLE's id map changes,
-        # and what the device saw there is the id of one of the oracle's neighbouring pixels (fp32 moved an edge by less
-        # than a pixel; it did not invent or lose a surface)
+        # ... and every one of them sits on a silhouette or a seam: 8-adjacent to a pixel where the ORACLE's id map changes, and
+        # what the device saw there is either (a) the surface one of the oracle's neighbouring pixels shows — fp32 moved a
+        # silhouette by less than a pixel — or (b) a surface that MEETS the oracle's at that point (|dt| within the t
+        # tolerance): the shared edge of two faces of a box or of two walls, where the reference's own tie rule decides by
+        # the last bit of t.  fp32 neither invents nor loses a surface.
         pad = np.pad(oid, 1, mode="edge")
         neigh = np.stack([pad[1 + dy:1 + dy + H, 1 + dx:1 + dx + W] for dy in (-1, 0, 1) for dx in (-1, 0, 1)])
         on_edge = (neigh != oid[None]).any(axis=0)
         assert on_edge[mism].all(), f"{(mism & ~on_edge).sum()} mismatching pixels are not on an id edge of the oracle map"
-        assert (neigh == gid[None]).any(axis=0)[mism].all(), "a mismatching pixel shows an id none of its oracle neighbours has"
+        silhouette = (neigh == gid[None]).any(axis=0)
+        seam = (gid != MISS) & (oid != MISS) & (np.abs(gt - ot) <= 2e-3 * np.maximum(1.0, np.abs(ot)))
+        bad = mism & ~(silhouette | seam)
+        detail = [(int(y), int(x), int(gid[y, x]), int(oid[y, x]), float(gt[y, x]), float(ot[y, x]), neigh[:, y, x].tolist())
+                  for y, x in list(zip(*np.nonzero(bad)))[:8]]
+        assert not bad.any(), f"{bad.sum()} mismatching pixels are neither a shifted silhouette nor a seam: {detail}"
         ok = ~mism & (oid != MISS)
         assert (np.abs(gt - ot)[ok] <= 2e-3 * np.maximum(1.0, np.abs(ot[ok]))).all()
         assert np.abs(gn - on)[ok].max() <= 2e-3
