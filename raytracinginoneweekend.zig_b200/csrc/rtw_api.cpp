@@ -97,7 +97,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
                                     "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE", "RTW_BVH_WIDE",
-                                    "RTW_FLAT_REGEN", "RTW_BOX_PRIMS"};
+                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS"};
 struct Options {
     std::map<std::string, std::string> v;
     const char *get(const char *name) const {
@@ -216,6 +216,18 @@ void free_images(rtw_ctx *c) {
 // (hittable.zig:203-217); rects padded +-1e-4 on the thin axis (hittable.zig:305-316, 358-369,
 // 411-422); RotateY = box of the 8 rotated corners (hittable.zig:516-556); Translate shifts
 // (hittable.zig:491-498).
+// Production rect tests evaluate t = (k - o) * rcp(d) and p = o + t d in fp32 with a 1-ulp reciprocal, so a ray aimed
+// EXACTLY at the shared edge of two abutting rects (Cornell's wall/floor seams seen from the symmetric camera: pixel
+// centres on the image diagonals) can land a few 1e-5 outside both and leak through (found by the seam check of
+// tests/test_gpu_parity.py: 63 of 360 000 parity-mode pixels).  The fp32 records therefore carry in-plane bounds widened
+// by 2^-19 of the rect's own coordinate magnitude — below the rounding noise of the test itself, invisible in the image,
+// and watertight.  The f64 tables of the reference-order probe keep the exact bounds.
+double rect_slack(const rtw_prim &p) {
+    double mag = 1.0;
+    for (int a = 0; a < 5; ++a) mag = std::max(mag, std::fabs(p.v[a]));
+    return mag * 1.9073486328125e-6;
+}
+
 Box3d leaf_box(const rtw_scene_desc *s, const rtw_prim &p) {
     Box3d b{};
     auto set = [&](double x0, double y0, double z0, double x1, double y1, double z1) {
@@ -241,9 +253,10 @@ Box3d leaf_box(const rtw_scene_desc *s, const rtw_prim &p) {
             }
             break;
         }
-        case RTW_PRIM_XY_RECT: set(p.v[0], p.v[2], p.v[4] - 0.0001, p.v[1], p.v[3], p.v[4] + 0.0001); break;
-        case RTW_PRIM_XZ_RECT: set(p.v[0], p.v[4] - 0.0001, p.v[2], p.v[1], p.v[4] + 0.0001, p.v[3]); break;
-        default: set(p.v[4] - 0.0001, p.v[0], p.v[2], p.v[4] + 0.0001, p.v[1], p.v[3]); break;
+        // rects: thin axis padded by 1e-4 as the reference does; in-plane extent = the widened bounds of the fp32 record
+        case RTW_PRIM_XY_RECT: { const double e = rect_slack(p); set(p.v[0] - e, p.v[2] - e, p.v[4] - 0.0001, p.v[1] + e, p.v[3] + e, p.v[4] + 0.0001); break; }
+        case RTW_PRIM_XZ_RECT: { const double e = rect_slack(p); set(p.v[0] - e, p.v[4] - 0.0001, p.v[2] - e, p.v[1] + e, p.v[4] + 0.0001, p.v[3] + e); break; }
+        default: { const double e = rect_slack(p); set(p.v[4] - 0.0001, p.v[0] - e, p.v[2] - e, p.v[4] + 0.0001, p.v[1] + e, p.v[3] + e); break; }
     }
     for (int x = p.xform; x >= 0; x = s->xforms[x].outer) {  // innermost -> outermost
         const rtw_xform &xf = s->xforms[x];
@@ -742,7 +755,8 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             d.b = make_float4(vel[0], vel[1], vel[2], 0.f);
             meta = PK_SPHERE;
         } else {
-            d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
+            const double e = rect_slack(p);  // watertight seams, see rect_slack
+            d.a = make_float4((float)(p.v[0] - e), (float)(p.v[1] + e), (float)(p.v[2] - e), (float)(p.v[3] + e));
             const int slot = p.xform >= 0 ? xform_slot_of(p.xform) : -1;
             d.b = make_float4((float)p.v[4], bits_to_float((uint32_t)slot), 0.f, 0.f);
             meta = p.kind == RTW_PRIM_XY_RECT ? PK_XY : p.kind == RTW_PRIM_XZ_RECT ? PK_XZ : PK_YZ;
@@ -897,6 +911,70 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                 } else { mov.push_back(dummy); mov.push_back(zero4); ids.push_back(0); }
             }
         }
+        // boxes: rects of one instance that are faces of ONE axis-aligned box (exact equality of the f64 fields) are
+        // scanned as three slabs (box_face in rtw_trace.cuh).  Found from pairs of differently oriented rects, which fix
+        // all six numbers; a box needs at least three faces to be worth a record.  Option RTW_BOX_PRIMS=0 turns it off.
+        std::vector<float4> boxes4;
+        std::vector<char> boxed(n, 0);
+        if (ctx->opt.num("RTW_BOX_PRIMS", 1) != 0) {
+            struct Cand { double x0, x1, y0, y1, z0, z1; };
+            auto ranges = [&](uint32_t i, double (&lo)[3], double (&hi)[3], int &thin, double &k) {
+                const rtw_prim &p = s->prims[i];  // in-plane axes (a, b) and the thin axis per orientation
+                const int ax = p.kind == RTW_PRIM_XY_RECT ? 0 : p.kind == RTW_PRIM_XZ_RECT ? 0 : 1;
+                const int bx = p.kind == RTW_PRIM_XY_RECT ? 1 : 2;
+                thin = 3 - ax - bx;
+                for (int a = 0; a < 3; ++a) { lo[a] = NAN; hi[a] = NAN; }
+                lo[ax] = p.v[0]; hi[ax] = p.v[1]; lo[bx] = p.v[2]; hi[bx] = p.v[3];
+                k = p.v[4];
+            };
+            auto face_of = [&](uint32_t i, const Cand &c) -> int {  // face slot 0..5 (z1, z0, y1, y0, x1, x0) or -1
+                double lo[3], hi[3], k; int thin;
+                ranges(i, lo, hi, thin, k);
+                const double clo[3] = {c.x0, c.y0, c.z0}, chi[3] = {c.x1, c.y1, c.z1};
+                for (int a = 0; a < 3; ++a)
+                    if (a != thin && !(lo[a] == clo[a] && hi[a] == chi[a])) return -1;
+                if (k == chi[thin]) return 2 * (2 - thin);
+                if (k == clo[thin]) return 2 * (2 - thin) + 1;
+                return -1;
+            };
+            for (size_t ia = 0; ia < rect_ids.size(); ++ia) {
+                const uint32_t a = rect_ids[ia];
+                if (boxed[a]) continue;
+                for (size_t ib = ia + 1; ib < rect_ids.size(); ++ib) {
+                    const uint32_t b = rect_ids[ib];
+                    if (boxed[b] || s->prims[b].kind == s->prims[a].kind || s->prims[b].xform != s->prims[a].xform) continue;
+                    double la[3], ha[3], lb[3], hb[3], ka, kb; int ta, tb;
+                    ranges(a, la, ha, ta, ka); ranges(b, lb, hb, tb, kb);
+                    Cand c;
+                    double lo[3], hi[3];
+                    bool ok = true;
+                    for (int x = 0; x < 3; ++x) {  // every axis is in-plane for at least one of two differently oriented rects
+                        const bool ina = x != ta, inb = x != tb;
+                        if (ina && inb && !(la[x] == lb[x] && ha[x] == hb[x])) ok = false;
+                        lo[x] = ina ? la[x] : lb[x]; hi[x] = ina ? ha[x] : hb[x];
+                    }
+                    if (!ok || !(lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2])) continue;
+                    c = Cand{lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]};
+                    if (face_of(a, c) < 0 || face_of(b, c) < 0) continue;
+                    uint32_t ids6[6], mask = 0;
+                    for (size_t ic = ia; ic < rect_ids.size(); ++ic) {
+                        const uint32_t r3 = rect_ids[ic];
+                        if (boxed[r3] || s->prims[r3].xform != s->prims[a].xform) continue;
+                        const int f = face_of(r3, c);
+                        if (f >= 0 && !(mask & (1u << f))) { mask |= 1u << f; ids6[f] = r3; }
+                    }
+                    if (__builtin_popcount(mask) < 3) continue;
+                    for (int f = 0; f < 6; ++f) if (mask & (1u << f)) boxed[ids6[f]] = 1; else ids6[f] = 0;
+                    const int slot = s->prims[a].xform >= 0 ? xform_slot_of(s->prims[a].xform) : -1;
+                    boxes4.push_back(make_float4((float)c.x0, (float)c.x1, (float)c.y0, (float)c.y1));
+                    boxes4.push_back(make_float4((float)c.z0, (float)c.z1, bits_to_float((uint32_t)(slot + 1)), bits_to_float(mask)));
+                    boxes4.push_back(make_float4(bits_to_float(ids6[0]), bits_to_float(ids6[1]), bits_to_float(ids6[2]), bits_to_float(ids6[3])));
+                    boxes4.push_back(make_float4(bits_to_float(ids6[4]), bits_to_float(ids6[5]), 0.f, 0.f));
+                    break;
+                }
+            }
+            rect_ids.erase(std::remove_if(rect_ids.begin(), rect_ids.end(), [&](uint32_t i) { return boxed[i] != 0; }), rect_ids.end());
+        }
         // rect runs: equal (xform slot, orientation); transforms in order of first appearance, the runs of one
         // transform adjacent so the scan sets up the object-space ray once per instance
         std::vector<float4> runs;
@@ -945,12 +1023,15 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         fl.off_rect = fl.off_mov + (uint32_t)mov.size();
         fl.off_runs = fl.off_rect + (uint32_t)rect.size();
         fl.n_runs = (uint32_t)runs.size();
-        fl.off_ids = fl.off_runs + (uint32_t)runs.size();
+        fl.off_boxes = fl.off_runs + (uint32_t)runs.size();
+        fl.n_boxes = (uint32_t)(boxes4.size() / 4);
+        fl.off_ids = fl.off_boxes + (uint32_t)boxes4.size();
         blob.insert(blob.end(), sph.begin(), sph.end());
         blob.insert(blob.end(), big.begin(), big.end());
         blob.insert(blob.end(), mov.begin(), mov.end());
         blob.insert(blob.end(), rect.begin(), rect.end());
         blob.insert(blob.end(), runs.begin(), runs.end());
+        blob.insert(blob.end(), boxes4.begin(), boxes4.end());
         const size_t at = blob.size();
         blob.resize(at + ids.size() / 4);
         if (!ids.empty()) std::memcpy(&blob[at], ids.data(), ids.size() * 4);
@@ -1063,7 +1144,7 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     if (!cam || !p || !d_accum) return fail(ctx, 1, "null argument");
     if (p->width == 0 || p->height == 0) return fail(ctx, 1, "empty image");
     if (p->spp_end < p->spp_begin) return fail(ctx, 1, "spp_end < spp_begin");
-    if ((uint64_t)p->width * p->height > 0x7FFFFFFFull) return fail(ctx, 1, "image too large");
+    if ((uint64_t)p->width * p->height > 0x7FFFFFFFull || p->width > 0xFFFFu || p->height > 0xFFFFu) return fail(ctx, 1, "image too large");
     int variant = 0;
     if (int rc = pick_variant(ctx, p->variant, &variant)) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -1082,7 +1163,8 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     // Default: pooled kernel (warp-level path queue + one vector atomic per path).
     const char *env = ctx->opt.get("RTW_SPP_CHUNK");
     const bool env_set = env && *env;
-    const bool pooled = !(p->flags & RTW_FLAG_DETERMINISTIC) && !env_set;
+    // option RTW_FLAT_KERNEL=1: the first schedule of the pooled flat kernel (kept for A/B measurements)
+    const int pooled = ((p->flags & RTW_FLAG_DETERMINISTIC) || env_set) ? 0 : (ctx->opt.num("RTW_FLAT_KERNEL", 2) == 1 ? 1 : 2);
     const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
     if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (flat image %u B)", ctx->scene.flat.total_f4 * 16u);
     const int grid = per_sm * ctx->n_sms;

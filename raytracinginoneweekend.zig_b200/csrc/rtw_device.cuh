@@ -84,6 +84,11 @@ struct DevPerlin {
 //                inner loop is specialised per orientation and branch-free
 //   runs       : uint4 per run: (xform slot + 1 or 0 | kRunSameXform when the previous run has the same
 //                transform, PK_XY/XZ/YZ, first rect, count); the runs of one transform are adjacent
+//   boxes      : 4 x float4 per box: rects of one instance that are faces of ONE axis-aligned box of its object space —
+//                the reference's `Box` (6 faces, hittable.zig:429-470) and rooms like the Cornell box's five walls (faces
+//                missing is fine).  (x0, x1, y0, y1), (z0, z1, bits(xform slot + 1 or 0), bits(face mask)), six prim ids
+//                in Box.init order z1, z0, y1, y0, x1, x0 (hittable.zig:437-442) + 2 pad.  Tested as three slabs, see
+//                box_faces in rtw_trace.cuh; rects that belong to a box are not in the runs.
 //   ids        : uint32 prim id per member slot, in the order sph | big | mov
 // Unused member slots have r^2 = -1 (never hit).
 constexpr uint32_t kRunSameXform = 0x80000000u;
@@ -92,7 +97,7 @@ struct FlatLayout {
     uint32_t off_sph, off_big, off_mov, off_rect, off_ids;
     uint32_t total_f4;
     uint32_t n_sphere_real;  // for the event counters
-    uint32_t n_runs, off_runs, pad0, pad1, pad2;
+    uint32_t n_runs, off_runs, n_boxes, off_boxes, pad2;
 };
 
 struct DevScene {

@@ -193,6 +193,110 @@ __global__ void __launch_bounds__(kBlock, 9) k_megakernel_pooled(const DevScene 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Flat megakernel, second schedule (default for flat scenes): same pool, same scan, but the iteration is rotated so
+// that the two divergent halves of the old one — "shade the lanes that hit" and "regenerate the lanes that ended",
+// which between them cover the whole warp — share everything that is common to them:
+//
+//     scan                       all lanes                 closest hit of the 32 rays
+//     A  hit lanes: hit record, emitted light, attenuation, metal absorb test, dielectric candidates (shade_prepare)
+//        miss lanes: background;  ended lanes: one vector reduction into the frame
+//     B  ended lanes take the next path indices of the pool (ballot + popc)
+//     C  all lanes               ONE Philox block: counter (pixel, sample, bounce) — bounce 0 = a new camera ray —
+//                                and ONE evaluation of the shared sampling maps (make_draw)
+//     D  new lanes: camera ray;  scattering lanes: add the drawn part (scatter_finish)
+//
+// ncu on the first schedule (profiles/r01_l): regenerate 146 instructions at 14.6 lanes + shade/Philox ~270 at 6-19
+// lanes per scan of ~800; here Philox and the sin/cos/sqrt of the sampling run once per iteration at 32 lanes.
+// Samples are identical to every other kernel's (same counters, same maps): only the schedule differs.
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock, 9) k_megakernel_flat(const DevScene sc, const DevCamera cam, const DevRender rp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
+    stage_flat(sc, s_flat);
+    Counters<STATS> cn;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t pool_next = 0, pool_end = 0, pool_tx = 0, pool_ty = 0, pool_s0 = 0;
+    bool more = true;
+
+    float3 beta = make_float3(1.0f, 1.0f, 1.0f), L = make_float3(0.0f, 0.0f, 0.0f);
+    Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+    Pending pd{0.f, 0.f, 0.f, 0.f, 0u};
+    uint32_t bounce = 0, cur_sample = 0, pixel = 0, pij = 0;  // pij = i | j << 16
+    bool alive = false;
+    for (;;) {
+        // ---- B: hand new paths to lanes without one ----
+        bool fresh = false;
+        for (;;) {
+            const uint32_t need = __ballot_sync(0xffffffffu, !alive && !fresh);
+            if (!need) break;
+            if (pool_next == pool_end) {
+                if (!more) break;
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(rp.tile_counter, 1u);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= rp.n_batches) { more = false; break; }
+                const uint32_t sb = b / rp.n_tiles, tile = b - sb * rp.n_tiles;
+                pool_ty = tile / rp.tiles_x; pool_tx = tile - pool_ty * rp.tiles_x;
+                pool_s0 = rp.spp_begin + sb * rp.batch_spp;
+                pool_next = 0;
+                pool_end = 32u * min(rp.batch_spp, rp.spp_end - pool_s0);
+            }
+            const uint32_t take = min((uint32_t)__popc(need), pool_end - pool_next);
+            const uint32_t rank = __popc(need & lt_mask);
+            if (!alive && !fresh && rank < take) {
+                const uint32_t idx = pool_next + rank;
+                const uint32_t pl = idx & 31u;
+                const uint32_t i = pool_tx * 8 + (pl & 7), j = pool_ty * 4 + (pl >> 3);
+                if (i < rp.width && j < rp.height) {  // ragged edge tiles: the slot is consumed, no path starts
+                    pixel = j * rp.width + i;
+                    pij = i | (j << 16);
+                    cur_sample = pool_s0 + (idx >> 5);
+                    bounce = 0;
+                    fresh = true;
+                    cn.add(ST_PATHS);
+                }
+            }
+            pool_next += take;
+        }
+        if (!__any_sync(0xffffffffu, alive || fresh)) {
+            if (!more && pool_next == pool_end) break;
+            continue;
+        }
+        // ---- C: one Philox block and one evaluation of the sampling maps for the whole warp ----
+        const uint4 rn = philox4x32_10(make_uint4(pixel, cur_sample, bounce, 0u), rp.philox_keys);
+        const Draw dw = make_draw(rn, fresh);
+        // ---- D: finish the rays ----
+        if (fresh) {
+            r = camera_from_draw(cam, rp, pij & 0xFFFFu, pij >> 16, dw);
+            beta = make_float3(1.0f, 1.0f, 1.0f);
+            L = make_float3(0.0f, 0.0f, 0.0f);
+            alive = true;
+        } else if (alive) {
+            scatter_finish(r, pd, dw);
+        }
+        // ---- scan ----
+        const Hit h = closest_hit_flat<STATS>(r, alive, s_flat, sc.flat, sc, 0.001f, cn);
+        // ---- A: what the hit decides without randomness ----
+        if (alive) {
+            cn.add(ST_RAYS);
+            if (h.slot == kMiss) {  // main.zig:109-112
+                L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
+                alive = false;
+            } else {
+                const DevPrim prim = sc.prims_flat[h.slot];
+                ++bounce;
+                // depth exhausted: the next rayColor call returns black before intersecting (main.zig:105-108)
+                alive = shade_prepare<STATS>(sc, r, prim, h.slot, h.t, beta, L, pd, cn) && bounce < rp.max_depth;
+            }
+            if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
+        }
+    }
+    if (STATS) cn.flush(rp.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BVH megakernel (pooled): a per-lane state machine.  BVH traversals have very different lengths
 // (measured: 11.6 of 32 lanes active when every lane runs its traversal to completion before the warp
 // shades), so here the warp interleaves: lanes that are traversing take one traversal step per
@@ -441,14 +545,16 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from rtw_api.cpp through rtw_kernels.h)
 // ---------------------------------------------------------------------------------------------
-template <int VARIANT, bool STATS, bool POOLED>
+// POOLED: 0 = deterministic lane-owns-pixel kernel, 1 = pooled (flat: first schedule), 2 = flat second schedule
+template <int VARIANT, bool STATS, int POOLED>
 static auto mega_kernel_ptr() {
     if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS>;
+    else if constexpr (POOLED == 2) return k_megakernel_flat<STATS>;
     else if constexpr (POOLED) return k_megakernel_pooled<VARIANT, STATS>;
     else return k_megakernel<VARIANT, STATS>;
 }
 
-template <int VARIANT, bool STATS, bool POOLED>
+template <int VARIANT, bool STATS, int POOLED>
 static cudaError_t launch_mega_t(const DevScene &sc, const DevCamera &cam, const DevRender &rp, int grid,
                                  size_t smem, cudaStream_t st) {
     auto kern = mega_kernel_ptr<VARIANT, STATS, POOLED>();
@@ -464,17 +570,19 @@ static size_t mega_smem(int variant, const DevScene &sc) {
     return variant == VAR_FLAT ? (size_t)sc.flat.total_f4 * sizeof(float4) : 0;
 }
 
-cudaError_t launch_megakernel(int variant, bool stats, bool pooled, const DevScene &sc, const DevCamera &cam,
+cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st) {
     const size_t smem = mega_smem(variant, sc);
+    if (variant == VAR_BVH && pooled == 2) pooled = 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
-    RTW_CASE(VAR_FLAT, false, false); RTW_CASE(VAR_FLAT, true, false); RTW_CASE(VAR_FLAT, false, true); RTW_CASE(VAR_FLAT, true, true);
-    RTW_CASE(VAR_BVH, false, false); RTW_CASE(VAR_BVH, true, false); RTW_CASE(VAR_BVH, false, true); RTW_CASE(VAR_BVH, true, true);
+    RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
+    RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2);
+    RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
 #undef RTW_CASE
     return cudaErrorInvalidValue;
 }
 
-template <int VARIANT, bool STATS, bool POOLED>
+template <int VARIANT, bool STATS, int POOLED>
 static int occ_t(size_t smem) {
     auto kern = mega_kernel_ptr<VARIANT, STATS, POOLED>();
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -482,11 +590,13 @@ static int occ_t(size_t smem) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock, smem) == cudaSuccess ? n : 0;
 }
 
-int megakernel_ctas_per_sm(int variant, bool stats, bool pooled, const DevScene &sc) {
+int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc) {
     const size_t smem = mega_smem(variant, sc);
+    if (variant == VAR_BVH && pooled == 2) pooled = 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
-    RTW_CASE(VAR_FLAT, false, false); RTW_CASE(VAR_FLAT, true, false); RTW_CASE(VAR_FLAT, false, true); RTW_CASE(VAR_FLAT, true, true);
-    RTW_CASE(VAR_BVH, false, false); RTW_CASE(VAR_BVH, true, false); RTW_CASE(VAR_BVH, false, true); RTW_CASE(VAR_BVH, true, true);
+    RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
+    RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2);
+    RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
 #undef RTW_CASE
     return 0;
 }

@@ -21,9 +21,11 @@ struct ResolveArgs {
 };
 
 // rtw_kernels.cu (production arithmetic)
-cudaError_t launch_megakernel(int variant, bool stats, bool pooled, const DevScene &sc, const DevCamera &cam,
+// pooled: 0 = deterministic lane-owns-pixel kernel, 1 = pooled path queue (BVH state machine / flat first schedule),
+//         2 = flat second schedule (k_megakernel_flat); 2 means 1 for the BVH variant
+cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st);
-int megakernel_ctas_per_sm(int variant, bool stats, bool pooled, const DevScene &sc);
+int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc);
 cudaError_t launch_resolve(const ResolveArgs &a, cudaStream_t st);
 cudaError_t launch_probe(int variant, const DevScene &sc, uint32_t n, const float *rays, uint32_t *prim_id, float *t,
                          float *normal, float *uv, cudaStream_t st);

@@ -287,6 +287,21 @@ __device__ __forceinline__ void rect_run(float ok, float dk, float oa, float da,
     }
 }
 
+// One face of a box: the plane is crossed at t; the ray is inside the two OTHER slabs exactly while t is in [lo, hi]
+// (their entry/exit parameters), which is the in-plane bounds test of XyRect/XzRect/YzRect.hit (hittable.zig:283-287) with
+// the inequalities moved from positions to parameters: x0 <= o + t d <= x1  <=>  lo_x <= t <= hi_x.  Both ends inclusive
+// like the reference's; equal t goes to the larger prim id (its list order).  The parameters two faces compare are the SAME
+// floats, so at a shared edge at least one of them accepts: a box is watertight by construction.
+template <bool STATS>
+__device__ __forceinline__ void box_face(float t, float lo, float hi, bool present, uint32_t id, float t_min, FlatBest &best,
+                                         Counters<STATS> &cn) {
+    const bool hit = present & (t >= t_min) & (t <= best.t) & (t >= lo) & (t <= hi);
+    if (STATS) { if (hit) cn.add(ST_RECT_ACCEPTS); }
+    const bool take = hit && (t < best.t || best.id == kMiss || id > best.id);
+    best.t = take ? t : best.t;
+    best.id = take ? id : best.id;
+}
+
 template <bool STATS>
 __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const float4 *s, const FlatLayout &L,
                                                 const DevScene &sc, float t_min, Counters<STATS> &cn) {
@@ -349,6 +364,42 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
                 const float4 c1 = make_float4(fmaf(v1.x, r.time, a1.x), fmaf(v1.y, r.time, a1.y), fmaf(v1.z, r.time, a1.z), a1.w);
                 flat_static_pair<STATS>(r, add, inv_a, c0, c1, h ? id.z : id.x, h ? id.w : id.y, active, t_min, best, cn);
             }
+        }
+    }
+    // ---- boxes: up to six rects that are the faces of one axis-aligned box of an instance's object space (the reference's
+    //      Box, hittable.zig:429-470, and rooms): one transform, three slabs, six parameter comparisons ----
+    {
+        const float4 *bx = s + L.off_boxes;
+        for (uint32_t q = 0; q < L.n_boxes; ++q, bx += 4) {
+            const float4 A = bx[0], B = bx[1];
+            const uint4 I0 = *reinterpret_cast<const uint4 *>(bx + 2);
+            const uint2 I1 = *reinterpret_cast<const uint2 *>(bx + 3);
+            const uint32_t xf = __float_as_uint(B.z), mask = __float_as_uint(B.w);
+            float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+            if (xf) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
+                if (active) cn.add(ST_XFORM_APPS);
+                const DevXform x = sc.xforms[xf - 1u];
+                ox = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; oy = r.oy + x.ty; oz = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
+                dx = fmaf(x.c, r.dx, -x.s * r.dz); dz = fmaf(x.s, r.dx, x.c * r.dz);
+            }
+            if (active) cn.add(ST_RECT_TESTS, __popc(mask));
+            const float ix = rcp_approx(dx), iy = rcp_approx(dy), iz = rcp_approx(dz);
+            const float tx0 = (A.x - ox) * ix, tx1 = (A.y - ox) * ix;  // t = (k - o) / d, hittable.zig:279
+            const float ty0 = (A.z - oy) * iy, ty1 = (A.w - oy) * iy;
+            const float tz0 = (B.x - oz) * iz, tz1 = (B.y - oz) * iz;
+            // fminf/fmaxf drop a NaN (origin on a plane of a parallel ray): that slab then does not constrain
+            const float lox = fminf(tx0, tx1), hix = fmaxf(tx0, tx1);
+            const float loy = fminf(ty0, ty1), hiy = fmaxf(ty0, ty1);
+            const float loz = fminf(tz0, tz1), hiz = fmaxf(tz0, tz1);
+            const float xlo = fmaxf(loy, loz), xhi = fminf(hiy, hiz);  // inside the y and z slabs: the x faces' bounds
+            const float ylo = fmaxf(lox, loz), yhi = fminf(hix, hiz);
+            const float zlo = fmaxf(lox, loy), zhi = fminf(hix, hiy);
+            box_face<STATS>(tz1, zlo, zhi, active && (mask & 1u), I0.x, t_min, best, cn);
+            box_face<STATS>(tz0, zlo, zhi, active && (mask & 2u), I0.y, t_min, best, cn);
+            box_face<STATS>(ty1, ylo, yhi, active && (mask & 4u), I0.z, t_min, best, cn);
+            box_face<STATS>(ty0, ylo, yhi, active && (mask & 8u), I0.w, t_min, best, cn);
+            box_face<STATS>(tx1, xlo, xhi, active && (mask & 16u), I1.x, t_min, best, cn);
+            box_face<STATS>(tx0, xlo, xhi, active && (mask & 32u), I1.y, t_min, best, cn);
         }
     }
     // ---- rects: runs of equal (instance transform, orientation); consecutive runs of one instance (a box = three
@@ -608,7 +659,7 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, cons
         const int par = (int)floorf(s.px * k) + (int)floorf(s.py * k) + (int)floorf(s.pz * k);
         tx = sc.textures[(par & 1) ? tx.a : tx.b];
     }
-    if (tx.kind == 0u) return make_float3(tx.r, tx.g, tx.bl);  // solid texture.zig:46-55
+    if (tx.kind <= 1u) return make_float3(tx.r, tx.g, tx.bl);  // solid texture.zig:46-55 (a checker still here = nesting beyond the guard: refused at upload)
     if (tx.kind == 2u) {  // noise texture.zig:100-104
         cn.add(ST_TEX_NOISE);
         const float v = 0.5f * (1.0f + sinf(tx.scale * s.pz + 10.0f * perlin_turb(sc.perlins[tx.a], s.px, s.py, s.pz)));
@@ -637,93 +688,106 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, cons
 // ---------------------------------------------------------------------------------------------
 // Samplers: same distributions as rand.zig:22-40, rejection-free (no divergent loops).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float3 sample_unit_vector(float u1, float u2) {  // randomUnitVector rand.zig:38-40
-    const float z = 1.0f - 2.0f * u1;
-    const float rxy = sqrt_approx(fmaxf(0.0f, 1.0f - z * z));
+// One Philox block per ray: block 0 of a (pixel, sample) feeds the camera ray, block b >= 1 the scatter at bounce b.
+// Both kinds of ray turn the block into the SAME intermediate — an angle (sin, cos of 2 pi ub) and a radius
+// (sqrt(ua) for the lens disk, sqrt(1 - z^2) with z = 1 - 2 ua for the unit vector) — so a warp whose lanes are partly
+// starting paths and partly scattering runs this once for all 32 lanes (k_megakernel_flat).
+//   ua, ub  lens-disk point (camera) | unit vector (diffuse, metal fuzz direction) | ua = the dielectric's uniform
+//   uc      pixel jitter u (camera)  | fuzz radius^3 (metal)
+//   ud      pixel jitter v (camera)
+//   ue      shutter time (camera): the low bytes of three words — bits no other variate uses
+struct Draw {
+    float ua, uc, ud, ue;
+    float x, y, z;  // camera: (x, y) = point in the unit disk; scatter: (x, y, z) = unit vector
+};
+// the maps themselves, from uniforms in [0,1):
+//   camera  (x, y) = sqrt(ua) (cos, sin)(2 pi ub): uniform in the unit disk          = randomPointInUnitDisk rand.zig:30-36
+//   else    z = 1 - 2 ua, (x, y) = sqrt(1 - z^2) (cos, sin)(2 pi ub): uniform on the sphere = randomUnitVector rand.zig:38-40
+//           and cbrt(uc) (x, y, z): uniform in the unit ball                             = randomPointInUnitSphere rand.zig:22-28
+__device__ __forceinline__ Draw draw_from(float ua, float ub, float uc, float ud, float ue, bool camera) {
+    Draw d;
+    d.ua = ua; d.uc = uc; d.ud = ud; d.ue = ue;
+    d.z = 1.0f - 2.0f * d.ua;
+    const float rad = sqrt_approx(camera ? d.ua : fmaxf(0.0f, fmaf(-d.z, d.z, 1.0f)));
     float sn, cs;
-    __sincosf(6.28318530717958647692f * u2, &sn, &cs);
-    return make_float3(rxy * cs, rxy * sn, z);
+    __sincosf(6.28318530717958647692f * ub, &sn, &cs);
+    d.x = rad * cs; d.y = rad * sn;
+    return d;
 }
-__device__ __forceinline__ float3 sample_unit_ball(float u1, float u2, float u3) {  // randomPointInUnitSphere rand.zig:22-28
-    const float3 d = sample_unit_vector(u1, u2);
-    const float rad = cbrtf(u3);
-    return make_float3(d.x * rad, d.y * rad, d.z * rad);
-}
-__device__ __forceinline__ float2 sample_unit_disk(float u1, float u2) {  // randomPointInUnitDisk rand.zig:30-36
-    const float rad = sqrt_approx(u1);
-    float sn, cs;
-    __sincosf(6.28318530717958647692f * u2, &sn, &cs);
-    return make_float2(rad * cs, rad * sn);
+__device__ __forceinline__ Draw make_draw(const uint4 rn, bool camera) {
+    return draw_from(u01_24(rn.x), u01_24(rn.y), u01_24(rn.z), u01_24(rn.w),
+                     u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8)), camera);
 }
 
-// The five uniforms of one camera ray — pixel jitter (ju, jv), lens disk (l1, l2), shutter time (tm) — sliced out of
-// the 128 bits of ONE Philox block: four 24-bit values from the high bits of the four words, the fifth from the low
-// bytes of the first three (disjoint bits, so the five are independent).
+// The five uniforms of one camera ray in the order (ju, jv, l1, l2, tm): pixel jitter, lens disk, shutter time.
 __device__ __forceinline__ void camera_uniforms(const DevRender &rp, uint32_t pixel, uint32_t sample, float (&u)[5]) {
     const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.philox_keys);
-    u[0] = u01_24(rn.x); u[1] = u01_24(rn.y); u[2] = u01_24(rn.z); u[3] = u01_24(rn.w);
+    u[0] = u01_24(rn.z); u[1] = u01_24(rn.w); u[2] = u01_24(rn.x); u[3] = u01_24(rn.y);
     u[4] = u01_24((rn.x << 24) | ((rn.y & 0xFFu) << 16) | ((rn.z & 0xFFu) << 8));
 }
 
-// Camera.getRay main.zig:91-100 + the (u,v) jitter of main.zig:390-391.
-__device__ __forceinline__ Ray camera_ray(const DevCamera &cam, const DevRender &rp, uint32_t pixel, uint32_t i,
-                                          uint32_t j, uint32_t sample) {
-    float un[5];
-    camera_uniforms(rp, pixel, sample, un);
-    const float ju = un[0], jv = un[1], l1 = un[2], l2 = un[3], tm = un[4];
-    const float s = ((float)i + ju) * rp.inv_wm1;  // main.zig:390-391 (division by W-1 as a multiply)
-    const float t = ((float)j + jv) * rp.inv_hm1;
-    const float2 dk = sample_unit_disk(l1, l2);
-    const float rdx = dk.x * cam.lens_radius, rdy = dk.y * cam.lens_radius;
+// Camera.getRay main.zig:91-100 + the (u,v) jitter of main.zig:390-391, from a drawn block.
+__device__ __forceinline__ Ray camera_from_draw(const DevCamera &cam, const DevRender &rp, uint32_t i, uint32_t j, const Draw &dw) {
+    const float s = ((float)i + dw.uc) * rp.inv_wm1;  // main.zig:390-391 (division by W-1 as a multiply)
+    const float t = ((float)j + dw.ud) * rp.inv_hm1;
+    const float rdx = dw.x * cam.lens_radius, rdy = dw.y * cam.lens_radius;
     const float offx = cam.ux * rdx + cam.wx * rdy, offy = cam.uy * rdx + cam.wy * rdy, offz = cam.uz * rdx + cam.wz * rdy;
     Ray r;
     r.ox = cam.ox + offx; r.oy = cam.oy + offy; r.oz = cam.oz + offz;
     r.dx = fmaf(cam.vx, t, fmaf(cam.hx, s, cam.lx)) - cam.ox - offx;
     r.dy = fmaf(cam.vy, t, fmaf(cam.hy, s, cam.ly)) - cam.oy - offy;
     r.dz = fmaf(cam.vz, t, fmaf(cam.hz, s, cam.lz)) - cam.oz - offz;
-    r.time = fmaf(tm, cam.time1 - cam.time0, cam.time0);
+    r.time = fmaf(dw.ue, cam.time1 - cam.time0, cam.time0);
     return r;
+}
+__device__ __forceinline__ Ray camera_ray(const DevCamera &cam, const DevRender &rp, uint32_t pixel, uint32_t i,
+                                          uint32_t j, uint32_t sample) {
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.philox_keys);
+    return camera_from_draw(cam, rp, i, j, make_draw(rn, true));
 }
 
 // ---------------------------------------------------------------------------------------------
-// One level of rayColor (main.zig:103-122) made iterative: `beta` is the product of attenuations
-// so far, `L` the radiance gathered.  Returns true when the path continues with `r` replaced by the
-// scattered ray.
+// One level of rayColor (main.zig:103-122) made iterative: `beta` is the product of attenuations so far, `L` the
+// radiance gathered.  Split around the random draw:
+//   shade_prepare  everything Material.emitted / scatter decide WITHOUT randomness: hit record, emitted light, the
+//                  attenuation (texture lookup), the metal absorb test, the dielectric's two candidate directions.
+//                  Leaves the next ray half-built in `r` (origin = hit point, direction = the deterministic part) and
+//                  the rest in `Pending`.  Returns false when the path ends here.
+//   scatter_finish adds the drawn part: n + unit vector | reflected + fuzz * ball point | reflect-or-refract by xi.
 // ---------------------------------------------------------------------------------------------
+struct Pending {
+    float bx, by, bz;  // dielectric: the refracted direction (r.d holds the reflected one)
+    float s;           // metal: fuzz; dielectric: Schlick reflectance (1 when refraction is impossible: xi < 1 never exceeds it)
+    uint32_t kind;     // RTW_MAT_* of the surface being left
+};
+
 template <bool STATS>
-__device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, Ray &r, const DevPrim &prim,
-                                      uint32_t prim_id, float t, uint32_t pixel, uint32_t sample, uint32_t bounce,
-                                      float3 &beta, float3 &L, Counters<STATS> &cn) {
+__device__ __forceinline__ bool shade_prepare(const DevScene &sc, Ray &r, const DevPrim &prim, uint32_t prim_id, float t,
+                                              float3 &beta, float3 &L, Pending &pd, Counters<STATS> &cn) {
     const Surface s = finalise_hit<STATS>(r, prim, t, sc, cn);
     const DevMaterial m = sc.materials[sc.prim_material[prim_id]];
+    pd.kind = m.kind;
     if (m.kind == 3u) {  // diffuse_light: emitted on both faces, never scatters (material.zig:97-109)
         cn.add(ST_EMIT);
         const float3 e = texture_value<STATS>(sc, m.tex, s, cn);
         L.x = fmaf(beta.x, e.x, L.x); L.y = fmaf(beta.y, e.y, L.y); L.z = fmaf(beta.z, e.z, L.z);
         return false;
     }
-    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.philox_keys);
-    float ndx, ndy, ndz;
-    if (m.kind == 0u) {  // diffuse material.zig:44-52
+    if (m.kind == 0u) {  // diffuse material.zig:44-52: direction = normal + unit vector
         cn.add(ST_SC_DIFFUSE);
-        const float3 uv = sample_unit_vector(u01_24(rn.x), u01_24(rn.y));
-        ndx = s.nx + uv.x; ndy = s.ny + uv.y; ndz = s.nz + uv.z;
-        if (fabsf(ndx) < 1e-8f && fabsf(ndy) < 1e-8f && fabsf(ndz) < 1e-8f) { ndx = s.nx; ndy = s.ny; ndz = s.nz; }
         const float3 a = texture_value<STATS>(sc, m.tex, s, cn);
         beta.x *= a.x; beta.y *= a.y; beta.z *= a.z;
+        r.dx = s.nx; r.dy = s.ny; r.dz = s.nz;
     } else {
         const float dd = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
         const float inv_len = dd > 0.0f ? rsqrtf(dd) : 1.0f;  // Vec3.normalized vec.zig:33-40
         const float ux = r.dx * inv_len, uy = r.dy * inv_len, uz = r.dz * inv_len;
         const float udn = fmaf(ux, s.nx, fmaf(uy, s.ny, uz * s.nz));
+        const float rx = fmaf(-2.0f * udn, s.nx, ux), ry = fmaf(-2.0f * udn, s.ny, uy), rz = fmaf(-2.0f * udn, s.nz, uz);  // reflect material.zig:112-114
+        r.dx = rx; r.dy = ry; r.dz = rz;
         if (m.kind == 1u) {  // metal material.zig:59-65
             cn.add(ST_SC_METAL);
-            const float rx = fmaf(-2.0f * udn, s.nx, ux), ry = fmaf(-2.0f * udn, s.ny, uy), rz = fmaf(-2.0f * udn, s.nz, uz);
-            ndx = rx; ndy = ry; ndz = rz;
-            if (m.param > 0.0f) {
-                const float3 b = sample_unit_ball(u01_24(rn.x), u01_24(rn.y), u01_24(rn.z));
-                ndx = fmaf(m.param, b.x, rx); ndy = fmaf(m.param, b.y, ry); ndz = fmaf(m.param, b.z, rz);
-            }
+            pd.s = m.param;
             beta.x *= m.r; beta.y *= m.g; beta.z *= m.b;
             // absorbed iff the UN-fuzzed reflection points into the surface (material.zig:64)
             if (!(fmaf(rx, s.nx, fmaf(ry, s.ny, rz * s.nz)) > 0.0f)) return false;
@@ -737,18 +801,42 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, R
             r0 *= r0;
             const float om = 1.0f - cos_theta, om2 = om * om;
             const float refl = fmaf(1.0f - r0, om2 * om2 * om, r0);  // Schlick material.zig:87-91
-            if (can_refract && refl < u01_24(rn.x)) {  // refract material.zig:116-121
-                const float px = ratio * fmaf(cos_theta, s.nx, ux), py = ratio * fmaf(cos_theta, s.ny, uy),
-                            pz = ratio * fmaf(cos_theta, s.nz, uz);
-                const float par = -sqrt_approx(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
-                ndx = fmaf(par, s.nx, px); ndy = fmaf(par, s.ny, py); ndz = fmaf(par, s.nz, pz);
-            } else {  // reflect material.zig:112-114
-                ndx = fmaf(-2.0f * udn, s.nx, ux); ndy = fmaf(-2.0f * udn, s.ny, uy); ndz = fmaf(-2.0f * udn, s.nz, uz);
-            }
+            pd.s = can_refract ? refl : 1.0f;                         // refract iff can_refract && refl < xi (material.zig:81)
+            const float px = ratio * fmaf(cos_theta, s.nx, ux), py = ratio * fmaf(cos_theta, s.ny, uy),
+                        pz = ratio * fmaf(cos_theta, s.nz, uz);       // refract material.zig:116-121
+            const float par = -sqrt_approx(fabsf(1.0f - fmaf(px, px, fmaf(py, py, pz * pz))));
+            pd.bx = fmaf(par, s.nx, px); pd.by = fmaf(par, s.ny, py); pd.bz = fmaf(par, s.nz, pz);
         }
     }
-    r.ox = s.px; r.oy = s.py; r.oz = s.pz;
-    r.dx = ndx; r.dy = ndy; r.dz = ndz;  // time is kept (material.zig:49)
+    r.ox = s.px; r.oy = s.py; r.oz = s.pz;  // time is kept (material.zig:49)
+    return true;
+}
+
+__device__ __forceinline__ void scatter_finish(Ray &r, const Pending &pd, const Draw &dw) {
+    if (pd.kind == 0u) {  // diffuse: normal + randomUnitVector, the normal alone if that sum is near zero (material.zig:45-48)
+        const float ndx = r.dx + dw.x, ndy = r.dy + dw.y, ndz = r.dz + dw.z;
+        const bool tiny = fabsf(ndx) < 1e-8f && fabsf(ndy) < 1e-8f && fabsf(ndz) < 1e-8f;
+        r.dx = tiny ? r.dx : ndx; r.dy = tiny ? r.dy : ndy; r.dz = tiny ? r.dz : ndz;
+    } else if (pd.kind == 1u) {  // metal: reflected + fuzz * randomPointInUnitSphere (material.zig:62)
+        if (pd.s > 0.0f) {
+            const float k = pd.s * cbrtf(dw.uc);
+            r.dx = fmaf(k, dw.x, r.dx); r.dy = fmaf(k, dw.y, r.dy); r.dz = fmaf(k, dw.z, r.dz);
+        }
+    } else if (pd.s < dw.ua) {  // dielectric: refract when Schlick's reflectance is below the uniform (material.zig:81)
+        r.dx = pd.bx; r.dy = pd.by; r.dz = pd.bz;
+    }
+}
+
+// prepare + draw + finish in one call (deterministic, BVH and wavefront kernels, unit probe).  Returns true when the
+// path continues with `r` replaced by the scattered ray.
+template <bool STATS>
+__device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, Ray &r, const DevPrim &prim,
+                                      uint32_t prim_id, float t, uint32_t pixel, uint32_t sample, uint32_t bounce,
+                                      float3 &beta, float3 &L, Counters<STATS> &cn) {
+    Pending pd;
+    if (!shade_prepare<STATS>(sc, r, prim, prim_id, t, beta, L, pd, cn)) return false;
+    const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.philox_keys);
+    scatter_finish(r, pd, make_draw(rn, false));
     return true;
 }
 

@@ -1,6 +1,6 @@
 // rtw_unit.cu — unit-level probes of the production STOCHASTIC device code (parity instruments, not timed).
 //
-// The image gates of the parity suite see camera_ray / sample_unit_* / shade only through converged means; these
+// The image gates of the parity suite see camera_ray / the sampling maps / shade only through converged means; these
 // kernels call the very same __device__ functions the megakernels call (rtw_trace.cuh, same compile flags as
 // rtw_kernels.cu) for caller-chosen indices and hand back both the result AND the random choices it was made from,
 // so the host can replay Camera.getRay (src/main.zig:91-100) and Material.scatter (src/rtw/material.zig:22-110) in the
@@ -23,20 +23,23 @@ __global__ void __launch_bounds__(128) k_unit_camera(const DevCamera cam, const 
     // the same slicing of the same Philox block as camera_ray (kept in one place: camera_uniforms)
     float u[5];
     camera_uniforms(rp, pixel, sample, u);
-    const float2 dk = sample_unit_disk(u[2], u[3]);
+    const Draw dw = make_draw(philox4x32_10(make_uint4(pixel, sample, 0u, 0u), rp.philox_keys), true);
+    const float2 dk = make_float2(dw.x, dw.y);  // the lens-disk point camera_ray used
     float *o = out + 14 * (size_t)k;
     o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.time;
     o[7] = u[0]; o[8] = u[1]; o[9] = u[2]; o[10] = u[3]; o[11] = u[4];
     o[12] = dk.x; o[13] = dk.y;
 }
 
-// out[n][8]: sample_unit_vector(u1,u2) | sample_unit_ball(u1,u2,u3) | sample_unit_disk(u1,u2)
+// out[n][8]: the maps of draw_from for caller-supplied uniforms: unit vector (u1,u2) | ball point (u1,u2,u3) | disk point (u1,u2)
 __global__ void __launch_bounds__(128) k_unit_samplers(uint32_t n, const float *__restrict__ u3, float *__restrict__ out) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float a = u3[3 * k], b = u3[3 * k + 1], c = u3[3 * k + 2];
-    const float3 v = sample_unit_vector(a, b), bl = sample_unit_ball(a, b, c);
-    const float2 d = sample_unit_disk(a, b);
+    const Draw sv = draw_from(a, b, c, 0.f, 0.f, false), sd = draw_from(a, b, c, 0.f, 0.f, true);
+    const float kr = cbrtf(sv.uc);  // scatter_finish: reflected + fuzz * cbrt(uc) * unit vector
+    const float3 v = make_float3(sv.x, sv.y, sv.z), bl = make_float3(kr * sv.x, kr * sv.y, kr * sv.z);
+    const float2 d = make_float2(sd.x, sd.y);
     float *o = out + 8 * (size_t)k;
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = bl.x; o[4] = bl.y; o[5] = bl.z; o[6] = d.x; o[7] = d.y;
 }
@@ -88,8 +91,9 @@ __global__ void __launch_bounds__(128) k_unit_shade(const DevScene sc, const Dev
     const DevMaterial m = sc.materials[sc.prim_material[id]];
     const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.philox_keys);
     float3 vec = make_float3(0.f, 0.f, 0.f);
-    if (m.kind == 0u) vec = sample_unit_vector(u01_24(rn.x), u01_24(rn.y));
-    else if (m.kind == 1u && m.param > 0.0f) vec = sample_unit_ball(u01_24(rn.x), u01_24(rn.y), u01_24(rn.z));
+    const Draw dw = make_draw(rn, false);  // what scatter_finish consumes
+    if (m.kind == 0u) vec = make_float3(dw.x, dw.y, dw.z);
+    else if (m.kind == 1u && m.param > 0.0f) { const float k = cbrtf(dw.uc); vec = make_float3(k * dw.x, k * dw.y, k * dw.z); }
     float3 beta = make_float3(1.f, 1.f, 1.f), L = make_float3(0.f, 0.f, 0.f);
     const bool go = shade<false>(sc, rp, r, prim, id, h.t, pixel, sample, bounce, beta, L, cn);
     o[0] = h.t;
