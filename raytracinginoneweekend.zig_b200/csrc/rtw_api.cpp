@@ -758,7 +758,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             const double e = rect_slack(p);  // watertight seams, see rect_slack
             d.a = make_float4((float)(p.v[0] - e), (float)(p.v[1] + e), (float)(p.v[2] - e), (float)(p.v[3] + e));
             const int slot = p.xform >= 0 ? xform_slot_of(p.xform) : -1;
-            d.b = make_float4((float)p.v[4], bits_to_float((uint32_t)slot), 0.f, 0.f);
+            d.b = make_float4((float)p.v[4], bits_to_float((uint32_t)slot), (float)e, 0.f);
             meta = p.kind == RTW_PRIM_XY_RECT ? PK_XY : p.kind == RTW_PRIM_XZ_RECT ? PK_XZ : PK_YZ;
         }
         d.b.w = bits_to_float(meta | (sphere_xf << 20));
@@ -969,7 +969,9 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                     boxes4.push_back(make_float4((float)c.x0, (float)c.x1, (float)c.y0, (float)c.y1));
                     boxes4.push_back(make_float4((float)c.z0, (float)c.z1, bits_to_float((uint32_t)(slot + 1)), bits_to_float(mask)));
                     boxes4.push_back(make_float4(bits_to_float(ids6[0]), bits_to_float(ids6[1]), bits_to_float(ids6[2]), bits_to_float(ids6[3])));
-                    boxes4.push_back(make_float4(bits_to_float(ids6[4]), bits_to_float(ids6[5]), 0.f, 0.f));
+                    const DevXform bxf = slot >= 0 ? xforms[slot] : DevXform{1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    boxes4.push_back(make_float4(bits_to_float(ids6[4]), bits_to_float(ids6[5]), bxf.c, bxf.s));
+                    boxes4.push_back(make_float4(bxf.tx, bxf.ty, bxf.tz, 0.f));
                     break;
                 }
             }
@@ -1024,7 +1026,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         fl.off_runs = fl.off_rect + (uint32_t)rect.size();
         fl.n_runs = (uint32_t)runs.size();
         fl.off_boxes = fl.off_runs + (uint32_t)runs.size();
-        fl.n_boxes = (uint32_t)(boxes4.size() / 4);
+        fl.n_boxes = (uint32_t)(boxes4.size() / kBoxF4);
         fl.off_ids = fl.off_boxes + (uint32_t)boxes4.size();
         blob.insert(blob.end(), sph.begin(), sph.end());
         blob.insert(blob.end(), big.begin(), big.end());
@@ -1164,7 +1166,10 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     const char *env = ctx->opt.get("RTW_SPP_CHUNK");
     const bool env_set = env && *env;
     // option RTW_FLAT_KERNEL=1: the first schedule of the pooled flat kernel (kept for A/B measurements)
-    const int pooled = ((p->flags & RTW_FLAG_DETERMINISTIC) || env_set) ? 0 : (ctx->opt.num("RTW_FLAT_KERNEL", 2) == 1 ? 1 : 2);
+    // 1 first schedule, 2 second schedule at 9 CTAs/SM (56 registers, spills), 3 (default) second schedule at 8 CTAs/SM
+    // (64 registers, no spills): measured 42.8 / 40.6 / 39.9 ms on scene 1 (1080p x 200 spp), 28.8 / 27.2 / 26.2 ms on C3
+    const long fk = ctx->opt.num("RTW_FLAT_KERNEL", 3);
+    const int pooled = ((p->flags & RTW_FLAG_DETERMINISTIC) || env_set) ? 0 : (fk == 1 ? 1 : fk == 2 ? 2 : 3);
     const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
     if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (flat image %u B)", ctx->scene.flat.total_f4 * 16u);
     const int grid = per_sm * ctx->n_sms;
@@ -1192,7 +1197,7 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     rp.n_sblocks = (spp + batch_spp - 1) / batch_spp;
     if ((uint64_t)rp.n_sblocks * rp.n_tiles > 0xFFFFFFF0ull) return fail(ctx, 1, "too many path batches for one launch");
     rp.n_batches = rp.n_sblocks * rp.n_tiles;
-    rp.service_threshold = 20; rp.steps_per_round = 2; rp.leaf_threshold = 8;  // tuned on the 485-sphere scene
+    rp.service_threshold = 24; rp.steps_per_round = 3; rp.leaf_threshold = 4;  // swept on the 10^6- and the 485-sphere scene (tools/bvh_sweep.py): -3 % / -1 % vs (20, 2, 8)
     rp.leaf_threshold = (uint32_t)std::max(1l, std::min(32l, ctx->opt.num("RTW_BVH_LEAF", rp.leaf_threshold)));
     rp.service_threshold = (uint32_t)std::max(1l, std::min(32l, ctx->opt.num("RTW_BVH_THRESH", rp.service_threshold)));
     rp.steps_per_round = (uint32_t)std::max(1l, std::min(64l, ctx->opt.num("RTW_BVH_STEPS", rp.steps_per_round)));

@@ -22,8 +22,8 @@ enum : uint32_t { PK_SPHERE = 0, PK_XY = 2, PK_XZ = 3, PK_YZ = 4 };
 struct __align__(16) DevPrim {
     // sphere: a = (cbx, cby, cbz, r)   centre(time) = cb + vel*time   (moving: hittable.zig:219-221)
     //         b = (vx, vy, vz, meta)   meta = PK_SPHERE | (big_index+1) << 8
-    // rect:   a = (a0, a1, b0, b1)     in-plane bounds
-    //         b = (k, bits(xform index or -1), 0, meta)
+    // rect:   a = (a0, a1, b0, b1)     in-plane bounds, widened by `slack` on every side (watertight seams)
+    //         b = (k, bits(xform index or -1), slack, meta)
     float4 a, b;
 };
 
@@ -84,14 +84,16 @@ struct DevPerlin {
 //                inner loop is specialised per orientation and branch-free
 //   runs       : uint4 per run: (xform slot + 1 or 0 | kRunSameXform when the previous run has the same
 //                transform, PK_XY/XZ/YZ, first rect, count); the runs of one transform are adjacent
-//   boxes      : 4 x float4 per box: rects of one instance that are faces of ONE axis-aligned box of its object space —
+//   boxes      : kBoxF4 x float4 per box: rects of one instance that are faces of ONE axis-aligned box of its object space —
 //                the reference's `Box` (6 faces, hittable.zig:429-470) and rooms like the Cornell box's five walls (faces
-//                missing is fine).  (x0, x1, y0, y1), (z0, z1, bits(xform slot + 1 or 0), bits(face mask)), six prim ids
-//                in Box.init order z1, z0, y1, y0, x1, x0 (hittable.zig:437-442) + 2 pad.  Tested as three slabs, see
-//                box_faces in rtw_trace.cuh; rects that belong to a box are not in the runs.
+//                missing is fine).  (x0, x1, y0, y1), (z0, z1, bits(xform slot + 1 or 0), bits(face mask)), four prim ids,
+//                (two prim ids, cos, sin), (tx, ty, tz, -): ids in Box.init order z1, z0, y1, y0, x1, x0
+//                (hittable.zig:437-442), the instance's composed transform inline.  Tested as three slabs, see box_face in
+//                rtw_trace.cuh; rects that belong to a box are not in the runs.
 //   ids        : uint32 prim id per member slot, in the order sph | big | mov
 // Unused member slots have r^2 = -1 (never hit).
 constexpr uint32_t kRunSameXform = 0x80000000u;
+constexpr uint32_t kBoxF4 = 5;
 struct FlatLayout {
     uint32_t n_sph_groups, n_big, n_mov_groups, n_rect;
     uint32_t off_sph, off_big, off_mov, off_rect, off_ids;

@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(kBlock, 9) k_megakernel_pooled(const DevScene 
 // lanes per scan of ~800; here Philox and the sin/cos/sqrt of the sampling run once per iteration at 32 lanes.
 // Samples are identical to every other kernel's (same counters, same maps): only the schedule differs.
 // ---------------------------------------------------------------------------------------------
-template <bool STATS>
-__global__ void __launch_bounds__(kBlock, 9) k_megakernel_flat(const DevScene sc, const DevCamera cam, const DevRender rp) {
+template <bool STATS, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_megakernel_flat(const DevScene sc, const DevCamera cam, const DevRender rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
     stage_flat(sc, s_flat);
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     prim_id[idx] = id; t_out[idx] = h.t;
     normal[3 * idx] = s.nx; normal[3 * idx + 1] = s.ny; normal[3 * idx + 2] = s.nz;
     if (uv) {
-        float u = s.u, v = s.v;
+        float u = __fdividef(s.u, s.ru), v = __fdividef(s.v, s.rv);  // rect: numerator / denominator (lazy division)
         if (s.is_sphere) {
             const float pi = 3.14159265358979323846f;
             u = (atan2f(-s.onz, s.onx) + pi) / (2.0f * pi);
@@ -545,11 +545,13 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from rtw_api.cpp through rtw_kernels.h)
 // ---------------------------------------------------------------------------------------------
-// POOLED: 0 = deterministic lane-owns-pixel kernel, 1 = pooled (flat: first schedule), 2 = flat second schedule
+// POOLED: 0 = deterministic lane-owns-pixel kernel, 1 = pooled (flat: first schedule), 2 = flat second schedule at 9 CTAs
+// per SM (56 registers, a few spills), 3 = the same at 8 CTAs per SM (64 registers)
 template <int VARIANT, bool STATS, int POOLED>
 static auto mega_kernel_ptr() {
     if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS>;
-    else if constexpr (POOLED == 2) return k_megakernel_flat<STATS>;
+    else if constexpr (POOLED == 3) return k_megakernel_flat<STATS, 8>;
+    else if constexpr (POOLED == 2) return k_megakernel_flat<STATS, 9>;
     else if constexpr (POOLED) return k_megakernel_pooled<VARIANT, STATS>;
     else return k_megakernel<VARIANT, STATS>;
 }
@@ -573,10 +575,10 @@ static size_t mega_smem(int variant, const DevScene &sc) {
 cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled == 2) pooled = 1;
+    if (variant == VAR_BVH && pooled >= 2) pooled = 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
-    RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2);
+    RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
 #undef RTW_CASE
     return cudaErrorInvalidValue;
@@ -592,10 +594,10 @@ static int occ_t(size_t smem) {
 
 int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled == 2) pooled = 1;
+    if (variant == VAR_BVH && pooled >= 2) pooled = 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
-    RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2);
+    RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
 #undef RTW_CASE
     return 0;

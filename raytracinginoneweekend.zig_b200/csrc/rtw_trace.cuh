@@ -192,8 +192,13 @@ struct FlatBest {
     uint32_t id;
 };
 
+// Candidates reach this with t <= b.t.  Ties go to the larger prim id; compared as SIGNED integers so that "no hit yet"
+// (kMiss = -1) loses against every id without a test of its own (prim ids stay below 2^28, the node-reference limit).
+__device__ __forceinline__ bool flat_better(const FlatBest &b, float t, uint32_t id) {
+    return t < b.t || (int32_t)id > (int32_t)b.id;
+}
 __device__ __forceinline__ void flat_consider(FlatBest &b, float t, uint32_t id) {
-    if (t < b.t || b.id == kMiss || id > b.id) { b.t = t; b.id = id; }
+    if (flat_better(b, t, id)) { b.t = t; b.id = id; }
 }
 
 // discriminant of the robust form (see sphere_test): returns disc', writes oc and bp
@@ -281,7 +286,7 @@ __device__ __forceinline__ void rect_run(float ok, float dk, float oa, float da,
         const bool hit = active && !(t < t_min || t > best.t || pa < a.x || pa > a.y || pb < a.z || pb > a.w);
         const uint32_t id = __float_as_uint(b.y);
         if (STATS) { if (hit) cn.add(ST_RECT_ACCEPTS); }
-        const bool take = hit && (t < best.t || best.id == kMiss || id > best.id);
+        const bool take = hit && flat_better(best, t, id);
         best.t = take ? t : best.t;
         best.id = take ? id : best.id;
     }
@@ -297,7 +302,7 @@ __device__ __forceinline__ void box_face(float t, float lo, float hi, bool prese
                                          Counters<STATS> &cn) {
     const bool hit = present & (t >= t_min) & (t <= best.t) & (t >= lo) & (t <= hi);
     if (STATS) { if (hit) cn.add(ST_RECT_ACCEPTS); }
-    const bool take = hit && (t < best.t || best.id == kMiss || id > best.id);
+    const bool take = hit && flat_better(best, t, id);
     best.t = take ? t : best.t;
     best.id = take ? id : best.id;
 }
@@ -370,17 +375,18 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
     //      Box, hittable.zig:429-470, and rooms): one transform, three slabs, six parameter comparisons ----
     {
         const float4 *bx = s + L.off_boxes;
-        for (uint32_t q = 0; q < L.n_boxes; ++q, bx += 4) {
+        for (uint32_t q = 0; q < L.n_boxes; ++q, bx += kBoxF4) {
             const float4 A = bx[0], B = bx[1];
             const uint4 I0 = *reinterpret_cast<const uint4 *>(bx + 2);
-            const uint2 I1 = *reinterpret_cast<const uint2 *>(bx + 3);
+            const float4 X = bx[3], T = bx[4];  // (id4, id5, cos, sin), (tx, ty, tz, -)
+            const uint2 I1 = make_uint2(__float_as_uint(X.x), __float_as_uint(X.y));
             const uint32_t xf = __float_as_uint(B.z), mask = __float_as_uint(B.w);
             float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
-            if (xf) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
+            if (xf) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573); the composed chain
+                       // sits in the record itself (same floats as DevScene::xforms[xf - 1], which finalise_hit reads)
                 if (active) cn.add(ST_XFORM_APPS);
-                const DevXform x = sc.xforms[xf - 1u];
-                ox = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; oy = r.oy + x.ty; oz = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
-                dx = fmaf(x.c, r.dx, -x.s * r.dz); dz = fmaf(x.s, r.dx, x.c * r.dz);
+                ox = fmaf(X.z, r.ox, -X.w * r.oz) + T.x; oy = r.oy + T.y; oz = fmaf(X.w, r.ox, X.z * r.oz) + T.z;
+                dx = fmaf(X.z, r.dx, -X.w * r.dz); dz = fmaf(X.w, r.dx, X.z * r.dz);
             }
             if (active) cn.add(ST_RECT_TESTS, __popc(mask));
             const float ix = rcp_approx(dx), iy = rcp_approx(dy), iz = rcp_approx(dz);
@@ -554,9 +560,10 @@ struct Surface {
     float px, py, pz;     // hit point, world space
     float nx, ny, nz;     // face-corrected normal (HitRecord.normal)
     float onx, ony, onz;  // outward normal (for sphere uv, hittable.zig:127)
-    float u, v;           // rect uv; sphere uv is computed lazily by the image texture
+    float u, v;           // sphere (instanced): final uv.  rect: numerators of uv, divided lazily by the image texture
+    float ru, rv;         // rect: denominators of uv (1 otherwise)
     bool front_face;
-    bool is_sphere;
+    bool is_sphere;       // plain sphere: uv = getSphereUv(outward normal), computed lazily by the image texture
 };
 
 template <bool STATS>
@@ -571,7 +578,7 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
         const float inv_r = rcp_approx(p.a.w);
         s.onx = (s.px - cx) * inv_r; s.ony = (s.py - cy) * inv_r; s.onz = (s.pz - cz) * inv_r;
         s.is_sphere = true;
-        s.u = 0.0f; s.v = 0.0f;
+        s.u = 0.0f; s.v = 0.0f; s.ru = 1.0f; s.rv = 1.0f;
         const uint32_t xf = __float_as_uint(p.b.w) >> 20;
         if (xf) {  // instanced sphere: getSphereUv sees the OBJECT-space normal (hittable.zig:127 inside Translate/RotateY)
             const DevXform x = sc.xforms[xf - 1];
@@ -598,8 +605,10 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
         if (kind == PK_XY) { pa = qx; pb = qy; nzo = 1.0f; }
         else if (kind == PK_XZ) { pa = qx; pb = qz; nyo = 1.0f; }
         else { pa = qy; pb = qz; nxo = 1.0f; }
-        s.u = __fdividef(pa - p.a.x, p.a.y - p.a.x);
-        s.v = __fdividef(pb - p.a.z, p.a.w - p.a.z);
+        // (x - x0) / (x1 - x0) hittable.zig:289-290, on the exact bounds: the record's are widened by `slack` (rtw_api.cpp
+        // rect_slack).  Kept un-divided: only an image texture ever reads u, v (texture_value divides there).
+        s.u = pa - (p.a.x + p.b.z); s.v = pb - (p.a.z + p.b.z);
+        s.ru = (p.a.y - p.a.x) - 2.0f * p.b.z; s.rv = (p.a.w - p.a.z) - 2.0f * p.b.z;
         // object -> world for the normal (RotateY.hit hittable.zig:588-590): n = A^T n_obj
         s.onx = fmaf(x.c, nxo, x.s * nzo);
         s.ony = nyo;
@@ -667,7 +676,7 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, cons
     }
     // image texture.zig:121-144 — nearest texel by truncation, alpha==0 -> (0,0,1)
     cn.add(ST_TEX_IMAGE);
-    float u = s.u, v = s.v;
+    float u = __fdividef(s.u, s.ru), v = __fdividef(s.v, s.rv);
     if (s.is_sphere) {  // getSphereUv hittable.zig:145-150
         const float pi = 3.14159265358979323846f;
         u = (atan2f(-s.onz, s.onx) + pi) / (2.0f * pi);

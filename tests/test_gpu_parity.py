@@ -214,6 +214,69 @@ def test_ties_later_element_wins(rtw, oracle, ctx):
     assert osc.trace_rays(rays, 64)[0].tolist() == [2, 4]
 
 
+def test_box_edges_and_corners(rtw, oracle, ctx):
+    """Rays aimed EXACTLY at the edges and corners of boxes (dyadic coordinates: every t is exact in fp32 and f64): all the
+    faces meeting there are hit at the same t and the reference's scan keeps the LAST one in Box.init order z1, z0, y1, y0,
+    x1, x0 (hittable.zig:437-442, 235-242).  The flat scan handles a box as three slabs (box records) and must reproduce that
+    — and a room with a missing face (five walls, the Cornell layout), entered through the opening, from inside and on its
+    seams.  Also checked: a box is watertight (a ray at an edge never slips between two faces)."""
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    b.box((0, 0, 0), (1, 2, 4), m)                      # prims 0..5: z1 z0 y1 y0 x1 x0
+    t = b.translate((8, 0, 0))
+    r = b.rotate_y(0.0, outer=t)                        # an instance chain with an exact (identity) rotation
+    b.box((0, 0, 0), (2, 2, 2), m, xform=r)             # prims 6..11
+    # room [16,32]^3 without its z0 wall, walls in the Cornell order: yz@x1, yz@x0, xz@y0, xz@y1, xy@z1   (prims 12..16)
+    b.rect(rtw.abi.PRIM_YZ_RECT, 16, 32, 16, 32, 32, m)
+    b.rect(rtw.abi.PRIM_YZ_RECT, 16, 32, 16, 32, 16, m)
+    b.rect(rtw.abi.PRIM_XZ_RECT, 16, 32, 16, 32, 16, m)
+    b.rect(rtw.abi.PRIM_XZ_RECT, 16, 32, 16, 32, 32, m)
+    b.rect(rtw.abi.PRIM_XY_RECT, 16, 32, 16, 32, 32, m)
+    desc = b.build()
+    ctx.upload_scene(desc, keep=desc)
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    rays = np.array([
+        [-1, -1, 1.5, 1, 1, 0, 0],      # edge x0/y0 of box 1 from outside: faces y0 (3), x0 (5) at t = 1       -> 5
+        [-1, 1, -1, 1, 0, 1, 0],        # edge x0/z0: faces z0 (1), x0 (5)                                       -> 5
+        [0.5, -1, -1, 0, 1, 1, 0],      # edge y0/z0: faces z0 (1), y0 (3)                                       -> 3
+        [-1, -1, -1, 1, 1, 1, 0],       # corner (0,0,0): z0 (1), y0 (3), x0 (5)                                 -> 5
+        [0.5, 1, 2, 0.5, 1, 2, 0],      # from inside to the corner (1,2,4): z1 (0), y1 (2), x1 (4) at t = 1     -> 4
+        [0.5, 1, 1.5, 0.5, 1, 0, 0],    # from inside to the edge x1/y1: y1 (2), x1 (4)                          -> 4
+        [7, -1, 1, 1, 1, 0, 0],         # instanced box: edge x0/y0 -> y0 (9), x0 (11)                            -> 11
+        [7, -1, -1, 1, 1, 1, 0],        # instanced box: corner                                                  -> 11
+        [24, 24, 0, 0, 0, 1, 0],        # room: in through the missing z0 wall, straight to the back wall        -> 16
+        [24, 24, 24, 8, -8, 0, 0],      # room from inside to the seam x1/y0: yz@x1 (12), xz@y0 (14) at t = 1     -> 14
+        [24, 24, 24, 8, 8, 8, 0],       # room corner (32,32,32): yz@x1 (12), xz@y1 (15), xy@z1 (16)              -> 16
+        [24, 24, 24, -8, -8, 0, 0],     # seam x0/y0: yz@x0 (13), xz@y0 (14)                                      -> 14
+        [24, 24, 24, 0, 0, -1, 0],      # out through the opening: nothing                                       -> miss
+        [40, 24, 24, -1, 0, 0, 0],      # from outside through the x1 wall (a rect has two faces)                 -> 12
+    ], dtype=np.float64)
+    want = [5, 5, 3, 5, 4, 4, 11, 11, 16, 14, 16, 14, MISS, 12]
+    assert osc.trace_rays(rays, 64)[0].tolist() == want
+    for precision in (32, 64, 0):
+        for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+            ids, t, _, _ = ctx.trace_rays(rays, precision, variant)
+            assert ids.tolist() == want, (precision, variant, ids.tolist())
+    # box records on and off trace the same surfaces (rays through random interior points of the three solids; rays aimed
+    # exactly AT edges graze by construction and are covered by the exact cases above)
+    rng = np.random.default_rng(8)
+    n = 40000
+    more = np.zeros((n, 7))
+    more[:, 0:3] = rng.uniform(-6, 40, (n, 3))
+    lo = np.array([[0, 0, 0], [8, 0, 0], [16, 16, 16]], dtype=np.float64)
+    hi = np.array([[1, 2, 4], [10, 2, 2], [32, 32, 32]], dtype=np.float64)
+    which = rng.integers(0, 3, n)
+    more[:, 3:6] = lo[which] + (hi[which] - lo[which]) * rng.uniform(0, 1, (n, 3)) - more[:, 0:3]
+    oid = osc.trace_rays(more, 64)[0]
+    with_boxes = ctx.trace_rays(more, 0, rtw.abi.VARIANT_MEGA_FLAT)
+    with ctx.options(RTW_BOX_PRIMS=0):
+        ctx.upload_scene(desc, keep=desc)
+        plain = ctx.trace_rays(more, 0, rtw.abi.VARIANT_MEGA_FLAT)
+    assert (with_boxes[0] != plain[0]).mean() < 1e-3 and (with_boxes[0] != oid).mean() < 1e-3 and (oid != MISS).mean() > 0.5
+    same = with_boxes[0] == plain[0]
+    assert np.abs(with_boxes[1] - plain[1])[same].max() < 1e-4
+
+
 def test_edge_cases(rtw, oracle, ctx):
     # empty scene: everything misses, the image is the background (resolve KAT: (.7,.8,1) -> 214,228,255)
     b = scene_util.DescBuilder()
