@@ -96,7 +96,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // Tuning knobs.  Each has an environment variable of the same name, read ONCE in rtw_cuda_create (never on the render
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
-                                    "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE", "RTW_BVH_WIDE",
+                                    "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE",
                                     "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS"};
 struct Options {
     std::map<std::string, std::string> v;

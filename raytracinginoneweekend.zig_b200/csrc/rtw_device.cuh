@@ -35,6 +35,7 @@ struct __align__(16) BvhNode {
 };
 constexpr uint32_t kNodeRefShift = 28, kNodeRefIndexMask = (1u << kNodeRefShift) - 1u;
 
+
 struct __align__(16) DevXform {
     // object = A*world + t with A = rotation about Y: x' = c*x - s*z, z' = s*x + c*z
     float c, s, tx, ty, tz, pad0, pad1, pad2;

@@ -575,7 +575,7 @@ static size_t mega_smem(int variant, const DevScene &sc) {
 cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled >= 2) pooled = 1;
+    if (variant == VAR_BVH && pooled >= 1) pooled = 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
@@ -594,7 +594,7 @@ static int occ_t(size_t smem) {
 
 int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled >= 2) pooled = 1;
+    if (variant == VAR_BVH && pooled >= 1) pooled = 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);

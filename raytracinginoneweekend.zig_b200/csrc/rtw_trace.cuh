@@ -35,6 +35,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const uint32_t (&keys)
 // 24-bit uniform in [0,1): exactly the fp32 lattice, never 1.0
 __device__ __forceinline__ float u01_24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 
+// 32 bytes per thread in ONE load instruction (LDG.E.256, new with sm_100): the BVH kernels fetch per-lane records from
+// scattered addresses, where the L1 data pipe serves one wavefront per lane per load INSTRUCTION — ncu on the 10^6-sphere
+// scene: l1tex__data_pipe_lsu_wavefronts at 77 % of peak with four LDG.128 per 64-byte sibling pair — so half as many
+// instructions is half as many wavefronts.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
 __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT, ~1 ulp, no slow path
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -491,7 +501,9 @@ struct BvhTraversal {
     __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
                                                   Counters<STATS> &cn) {
         const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
-        const float4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+        float4 l0, l1, r0, r1;
+        ldg256(q, l0, l1);
+        ldg256(q + 2, r0, r1);
         const BvhNode L{l0.x, l0.y, l0.z, __float_as_uint(l0.w), l1.x, l1.y, l1.z, __float_as_uint(l1.w)};
         const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
         cn.add(ST_NODE_TESTS, 2);
@@ -519,9 +531,8 @@ struct BvhTraversal {
         const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint32_t slot = at + i;
-            const float4 *pp = reinterpret_cast<const float4 *>(sc.prims_bvh + slot);
             DevPrim p;
-            p.a = __ldg(pp); p.b = __ldg(pp + 1);
+            ldg256(sc.prims_bvh + slot, p.a, p.b);
             float t;
             if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
                 const uint32_t id = __ldg(sc.bvh_prim_id + slot);

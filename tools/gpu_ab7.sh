@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out/r02
+python tools/ab.py 'c4:8:500:1920x1080x32:2' 'c4_wide:8:500:1920x1080x32:2:RTW_BVH_WIDE=1' \
+  'c2p:1:11:1920x1080x64:2' 'c2p_wide:1:11:1920x1080x64:2:RTW_BVH_WIDE=1' \
+  's1bvh:1:3:1920x1080x100:2' 'c4_sah:8:500:1920x1080x32:2:RTW_BVH_BUILDER=sah' > gpurun_out/r02/ab7.jsonl 2> gpurun_out/r02/ab7.err
+cut -c1-330 gpurun_out/r02/ab7.jsonl; tail -3 gpurun_out/r02/ab7.err
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -k "bvh or million or random_scene or primary or flat_and_bvh or ties or box_edges or negative or edge_cases" > gpurun_out/r02/pytest_ab9.log 2>&1; tail -8 gpurun_out/r02/pytest_ab9.log
