@@ -863,24 +863,78 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             for (int a = 0; a < 3; ++a) c[a] = p.v[a] + (p.v[3 + a] - p.v[a]) * u;
             return std::fabs(p.v[8]);
         };
-        auto bound_of = [&](const std::vector<uint32_t> &m) {
-            double cen[3] = {0, 0, 0};
-            for (uint32_t i : m)
-                for (int a = 0; a < 3; ++a) cen[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]) / (double)m.size();
-            double R = 0;
+        // Bound of a group = the smallest ball enclosing its members over the shutter interval (both end positions of a
+        // moving sphere; the sweep between them is a straight segment, covered by convexity).  Badoiu-Clarkson iteration
+        // from the centroid: step towards the farthest member by 1/(k+1).  A vote passes a group roughly in proportion to
+        // the cross-section R^2 of its bound, so a tighter ball is fewer member tests.
+        auto ball_of = [&](const std::vector<uint32_t> &m, double cen[3]) {
+            struct B { double c[3], r; };
+            std::vector<B> balls;
             for (uint32_t i : m)
                 for (double t : {s->time0, s->time1}) {
-                    double c[3];
-                    const double r = centre_at(i, t, c);
-                    const double d = std::sqrt((c[0] - cen[0]) * (c[0] - cen[0]) + (c[1] - cen[1]) * (c[1] - cen[1]) + (c[2] - cen[2]) * (c[2] - cen[2]));
-                    R = std::max(R, d + r);
+                    B b;
+                    b.r = centre_at(i, t, b.c);
+                    balls.push_back(b);
                 }
+            cen[0] = cen[1] = cen[2] = 0;
+            for (const B &b : balls) for (int a = 0; a < 3; ++a) cen[a] += b.c[a] / (double)balls.size();
+            auto radius_at = [&](const double c[3], size_t *far) {
+                double R = 0;
+                for (size_t k = 0; k < balls.size(); ++k) {
+                    const double d = std::sqrt((balls[k].c[0] - c[0]) * (balls[k].c[0] - c[0]) + (balls[k].c[1] - c[1]) * (balls[k].c[1] - c[1]) +
+                                               (balls[k].c[2] - c[2]) * (balls[k].c[2] - c[2])) + balls[k].r;
+                    if (d > R) { R = d; if (far) *far = k; }
+                }
+                return R;
+            };
+            double best[3] = {cen[0], cen[1], cen[2]}, best_R = radius_at(cen, nullptr), c[3] = {cen[0], cen[1], cen[2]};
+            for (int k = 1; k <= 400 && !balls.empty(); ++k) {
+                size_t far = 0;
+                const double R = radius_at(c, &far);
+                if (R < best_R) { best_R = R; best[0] = c[0]; best[1] = c[1]; best[2] = c[2]; }
+                const B &f = balls[far];
+                const double d = R - f.r;  // distance to the far ball's centre
+                if (!(d > 0)) break;
+                // the point of the far ball farthest from c lies on the ray c -> f.c at distance R
+                const double step = 1.0 / (k + 1.0);
+                for (int a = 0; a < 3; ++a) c[a] += step * (f.c[a] - c[a]) * (R / d);
+            }
+            cen[0] = best[0]; cen[1] = best[1]; cen[2] = best[2];
+            return best_R;
+        };
+        auto bound_of = [&](const std::vector<uint32_t> &m) {
+            double cen[3];
+            double R = ball_of(m, cen);
             R = R * (1.0 + 1e-5) + 1e-6;  // fp32 evaluation slack
             const float cf[3] = {(float)cen[0], (float)cen[1], (float)cen[2]};
             for (int a = 0; a < 3; ++a) R += std::fabs((double)cf[a] - cen[a]);
             return make_float4(cf[0], cf[1], cf[2], (float)(R * (1.0 + 1e-6)));  // the radius, not its square
         };
-        const auto sgroups = make_groups(stat_ids), mgroups = make_groups(mov_ids);
+        // Median splits give spatially compact groups; a few passes of pairwise member exchanges between groups then
+        // lower the sum of R^2 (deterministic: fixed order, strict improvement only).
+        auto refine_groups = [&](std::vector<std::vector<uint32_t>> &groups) {
+            if (groups.size() < 2 || groups.size() > 64) return;
+            std::vector<double> R2(groups.size());
+            double cen[3];
+            for (size_t g = 0; g < groups.size(); ++g) { const double R = ball_of(groups[g], cen); R2[g] = R * R; }
+            for (int pass = 0; pass < 4; ++pass) {
+                bool improved = false;
+                for (size_t g = 0; g < groups.size(); ++g)
+                    for (size_t h2 = g + 1; h2 < groups.size(); ++h2)
+                        for (size_t a = 0; a < groups[g].size(); ++a)
+                            for (size_t b2 = 0; b2 < groups[h2].size(); ++b2) {
+                                std::swap(groups[g][a], groups[h2][b2]);
+                                const double Rg = ball_of(groups[g], cen), Rh = ball_of(groups[h2], cen);
+                                if (Rg * Rg + Rh * Rh < (R2[g] + R2[h2]) * (1.0 - 1e-9)) { R2[g] = Rg * Rg; R2[h2] = Rh * Rh; improved = true; }
+                                else std::swap(groups[g][a], groups[h2][b2]);
+                            }
+                if (!improved) break;
+            }
+            for (auto &g : groups) std::sort(g.begin(), g.end());
+        };
+        auto sgroups = make_groups(stat_ids), mgroups = make_groups(mov_ids);
+        refine_groups(sgroups);
+        refine_groups(mgroups);
         std::vector<float4> sph, big, mov, rect;
         std::vector<uint32_t> ids;
         const float4 dummy = make_float4(0.f, 0.f, 0.f, -1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
