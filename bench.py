@@ -162,7 +162,7 @@ def config_dict(n_gpus, spp=SPP):
 S_WIDTH, S_HEIGHT, S_SPP = 3840, 2160, 1000  # BASELINE.json configs[4] / the north_star target
 
 
-def strong_scaling(ctx, hs, rank, local_rank, world, sync_all, reps=3):
+def strong_scaling(ctx, hs, rank, local_rank, world, sync_all, host_barrier, reps=3):
     """STRONG scaling on the record (the north_star target): ONE 3840x2160 frame of scene 1 at 1000 spp, depth 50, its
     samples split over the N GPUs, timed by the host's wall clock around whole frames (barrier + device
     synchronize on both sides, max over ranks), two ways:
@@ -207,6 +207,11 @@ def strong_scaling(ctx, hs, rank, local_rank, world, sync_all, reps=3):
                     "exchange": f"one ncclReduce of {W * H * 16 / 1e6:.1f} MB per rank onto rank 0, then resolve on rank 0" if world > 1 else "none"}}
     del accum
     peer = None
+    # The other ranks must leave their GPUs IDLE while rank 0 drives them: they wait on the host (gloo), not in an NCCL
+    # barrier — an NCCL kernel spinning on GPU g for rank 0 while rank 0's own kernels are queued on GPU g from another
+    # process is two contexts time-slicing one device around a kernel that cannot finish (B200_PROFILING.md warns of it).
+    torch.cuda.synchronize()
+    host_barrier()
     if rank == 0:
         try:
             group = rtw_b200.create_multi(world) if world > 1 else [ctx]
@@ -243,6 +248,7 @@ def strong_scaling(ctx, hs, rank, local_rank, world, sync_all, reps=3):
         except rtw_b200.RtwCudaError as e:  # e.g. no peer access between the devices of this box
             peer = {"unavailable": str(e)}
     out["peer"] = peer
+    host_barrier()
     sync_all()
     return out
 
@@ -276,9 +282,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")  # host-side barriers (no kernel on any GPU)
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
     spp = args.spp
     ctx = rtw_b200.Context(local_rank)
     hs = rtw_b200.HostScene(1, grid=GRID, seed=SEED)
@@ -375,7 +387,7 @@ def main():
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     rays_step, flops_step = float(sums[0]), float(sums[2])
 
-    strong = None if args.no_strong else strong_scaling(ctx, hs, rank, local_rank, world, sync_all)
+    strong = None if args.no_strong else strong_scaling(ctx, hs, rank, local_rank, world, sync_all, host_barrier)
 
     if rank == 0:
         peak_tf, peak_mhz = ctx.measure_fp32_peak()
