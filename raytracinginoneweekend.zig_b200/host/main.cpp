@@ -52,7 +52,7 @@ int main(int argc, char **argv) {
     void *h = dlopen(lib.c_str(), RTLD_NOW);
     if (!h) { fprintf(stderr, "cannot load %s: %s\n", lib.c_str(), dlerror()); return 1; }
 #define SYM(name) auto name##_ = reinterpret_cast<decltype(&name)>(dlsym(h, #name)); if (!name##_) { fprintf(stderr, "missing symbol %s\n", #name); return 1; }
-    SYM(rtw_cuda_create) SYM(rtw_cuda_destroy) SYM(rtw_cuda_last_error) SYM(rtw_cuda_upload_scene) SYM(rtw_cuda_render) SYM(rtw_cuda_render_multi) SYM(rtw_cuda_stats)
+    SYM(rtw_cuda_create) SYM(rtw_cuda_destroy) SYM(rtw_cuda_last_error) SYM(rtw_cuda_upload_scene) SYM(rtw_cuda_render) SYM(rtw_cuda_render_multi) SYM(rtw_cuda_create_multi) SYM(rtw_cuda_stats)
 
     SceneSetup s;
     try { s = makeScene(scene, grid, seed, asset); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return 1; }
@@ -63,11 +63,14 @@ int main(int argc, char **argv) {
     const FlatScene flat = flatten(s.world, 0, 1);
     const rtw_scene_desc desc = flat.desc();
 
+    // --gpus N: devices 0..N-1 with peer mappings between every pair (rtw_cuda_create_multi); else the one device asked for
     std::vector<rtw_ctx *> ctxs((size_t)(gpus > 1 ? gpus : 1), nullptr);
-    for (size_t g = 0; g < ctxs.size(); ++g) {
-        if (rtw_cuda_create_(device + (int)g, &ctxs[g])) { fprintf(stderr, "rtw_cuda_create: %s\n", rtw_cuda_last_error_(nullptr)); return 1; }
-        if (rtw_cuda_upload_scene_(ctxs[g], &desc)) { fprintf(stderr, "upload: %s\n", rtw_cuda_last_error_(ctxs[g])); return 1; }
+    if (gpus > 1 ? rtw_cuda_create_multi_((uint32_t)gpus, ctxs.data()) : rtw_cuda_create_(device, &ctxs[0])) {
+        fprintf(stderr, "rtw_cuda_create: %s\n", rtw_cuda_last_error_(nullptr));
+        return 1;
     }
+    for (size_t g = 0; g < ctxs.size(); ++g)
+        if (rtw_cuda_upload_scene_(ctxs[g], &desc)) { fprintf(stderr, "upload: %s\n", rtw_cuda_last_error_(ctxs[g])); return 1; }
     rtw_ctx *ctx = ctxs[0];
     rtw_render_params p{};
     p.width = s.image_width; p.height = s.image_height;
@@ -81,8 +84,8 @@ int main(int argc, char **argv) {
     rtw_stats st{};
     rtw_cuda_stats_(ctx, &st);
     const double paths = (double)p.width * p.height * s.samples_per_pixel;
-    fprintf(stderr, "scene %d: %u prims, %ux%u, %u spp, trace %.2f ms (%.1f Mpaths/s), resolve %.3f ms\n", scene, desc.n_prims,
-            p.width, p.height, s.samples_per_pixel, st.ms_trace, paths / (st.ms_trace * 1e3), st.ms_resolve);
+    fprintf(stderr, "scene %d: %u prims, %ux%u, %u spp on %zu GPU(s): %.2f ms wall (%.1f Mpaths/s); device 0: trace %.2f ms, resolve %.3f ms\n",
+            scene, desc.n_prims, p.width, p.height, s.samples_per_pixel, ctxs.size(), st.ms_wall, paths / (st.ms_wall * 1e3), st.ms_trace, st.ms_resolve);
     const bool png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;  // the reference writes out.png (main.zig:405)
     if (!(png ? writePng(out, image.data(), p.width, p.height) : writePpm(out, image.data(), p.width, p.height))) {
         fprintf(stderr, "cannot write %s\n", out.c_str());

@@ -99,6 +99,11 @@ pub extern "c" fn rtw_cuda_stats(ctx: *Ctx, out: *Stats) c_int;
 
 pub extern "c" fn rtw_cuda_create_multi(n_gpus: u32, out: [*]?*Ctx) c_int;
 pub extern "c" fn rtw_cuda_set_option(ctx: *Ctx, name: [*:0]const u8, value: ?[*:0]const u8) c_int;
+// parity probes of the stochastic device code (include/rtw_cuda.h): results + the random choices they were made from
+pub extern "c" fn rtw_cuda_unit_camera(ctx: *Ctx, cam: *const Camera, params: *const RenderParams, n: u32, ijs: [*]const u32, out: [*]f32) c_int;
+pub extern "c" fn rtw_cuda_unit_samplers(ctx: *Ctx, n: u32, u3: [*]const f32, out: [*]f32) c_int;
+pub extern "c" fn rtw_cuda_unit_uniforms(ctx: *Ctx, params: *const RenderParams, n: u32, psb: [*]const u32, out: [*]f32) c_int;
+pub extern "c" fn rtw_cuda_unit_shade(ctx: *Ctx, params: *const RenderParams, n: u32, rays: [*]const f64, psb: [*]const u32, prim_id: [*]u32, out: [*]f32) c_int;
 pub extern "c" fn rtw_cuda_render_multi(ctxs: [*]const ?*Ctx, n_ctx: u32, cam: *const Camera, params: *const RenderParams, rgb8_out: [*]u8) c_int;
 
 pub const Error = error{ CudaUnavailable, SceneRejected, RenderFailed };
