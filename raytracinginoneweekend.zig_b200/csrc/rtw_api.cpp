@@ -867,20 +867,27 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         // moving sphere; the sweep between them is a straight segment, covered by convexity).  Badoiu-Clarkson iteration
         // from the centroid: step towards the farthest member by 1/(k+1).  A vote passes a group roughly in proportion to
         // the cross-section R^2 of its bound, so a tighter ball is fewer member tests.
-        auto ball_of = [&](const std::vector<uint32_t> &m, double cen[3]) {
-            struct B { double c[3], r; };
-            std::vector<B> balls;
+        struct Ball { double c[3], r; };
+        auto balls_of = [&](const std::vector<uint32_t> &m, Ball *balls) {  // <= 8 balls: 4 members x both shutter ends
+            size_t nb = 0;
             for (uint32_t i : m)
                 for (double t : {s->time0, s->time1}) {
-                    B b;
+                    Ball b;
                     b.r = centre_at(i, t, b.c);
-                    balls.push_back(b);
+                    if (nb && balls[nb - 1].r == b.r && balls[nb - 1].c[0] == b.c[0] && balls[nb - 1].c[1] == b.c[1] && balls[nb - 1].c[2] == b.c[2])
+                        continue;  // a static sphere is one ball, not two
+                    balls[nb++] = b;
                 }
+            return nb;
+        };
+        auto ball_of = [&](const std::vector<uint32_t> &m, double cen[3], int iters = 400) {
+            Ball balls[8];
+            const size_t nb = balls_of(m, balls);
             cen[0] = cen[1] = cen[2] = 0;
-            for (const B &b : balls) for (int a = 0; a < 3; ++a) cen[a] += b.c[a] / (double)balls.size();
+            for (size_t k = 0; k < nb; ++k) for (int a = 0; a < 3; ++a) cen[a] += balls[k].c[a] / (double)nb;
             auto radius_at = [&](const double c[3], size_t *far) {
                 double R = 0;
-                for (size_t k = 0; k < balls.size(); ++k) {
+                for (size_t k = 0; k < nb; ++k) {
                     const double d = std::sqrt((balls[k].c[0] - c[0]) * (balls[k].c[0] - c[0]) + (balls[k].c[1] - c[1]) * (balls[k].c[1] - c[1]) +
                                                (balls[k].c[2] - c[2]) * (balls[k].c[2] - c[2])) + balls[k].r;
                     if (d > R) { R = d; if (far) *far = k; }
@@ -888,11 +895,11 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                 return R;
             };
             double best[3] = {cen[0], cen[1], cen[2]}, best_R = radius_at(cen, nullptr), c[3] = {cen[0], cen[1], cen[2]};
-            for (int k = 1; k <= 400 && !balls.empty(); ++k) {
+            for (int k = 1; k <= iters && nb; ++k) {
                 size_t far = 0;
                 const double R = radius_at(c, &far);
                 if (R < best_R) { best_R = R; best[0] = c[0]; best[1] = c[1]; best[2] = c[2]; }
-                const B &f = balls[far];
+                const Ball &f = balls[far];
                 const double d = R - f.r;  // distance to the far ball's centre
                 if (!(d > 0)) break;
                 // the point of the far ball farthest from c lies on the ray c -> f.c at distance R
@@ -901,6 +908,22 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             }
             cen[0] = best[0]; cen[1] = best[1]; cen[2] = best[2];
             return best_R;
+        };
+        // No enclosing ball is smaller than half the extent of any two members: a lower bound that costs 28 distances
+        // and rejects almost every exchange candidate of refine_groups before the iteration above runs.
+        auto ball_lower_bound = [&](const std::vector<uint32_t> &m) {
+            Ball balls[8];
+            const size_t nb = balls_of(m, balls);
+            double lb = 0;
+            for (size_t i = 0; i < nb; ++i) {
+                lb = std::max(lb, balls[i].r);
+                for (size_t j = i + 1; j < nb; ++j) {
+                    const double d = std::sqrt((balls[i].c[0] - balls[j].c[0]) * (balls[i].c[0] - balls[j].c[0]) + (balls[i].c[1] - balls[j].c[1]) * (balls[i].c[1] - balls[j].c[1]) +
+                                               (balls[i].c[2] - balls[j].c[2]) * (balls[i].c[2] - balls[j].c[2]));
+                    lb = std::max(lb, 0.5 * (d + balls[i].r + balls[j].r));
+                }
+            }
+            return lb;
         };
         auto bound_of = [&](const std::vector<uint32_t> &m) {
             double cen[3];
@@ -924,9 +947,18 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                         for (size_t a = 0; a < groups[g].size(); ++a)
                             for (size_t b2 = 0; b2 < groups[h2].size(); ++b2) {
                                 std::swap(groups[g][a], groups[h2][b2]);
-                                const double Rg = ball_of(groups[g], cen), Rh = ball_of(groups[h2], cen);
-                                if (Rg * Rg + Rh * Rh < (R2[g] + R2[h2]) * (1.0 - 1e-9)) { R2[g] = Rg * Rg; R2[h2] = Rh * Rh; improved = true; }
-                                else std::swap(groups[g][a], groups[h2][b2]);
+                                const double now = (R2[g] + R2[h2]) * (1.0 - 1e-9);
+                                bool better = false;
+                                const double Lg = ball_lower_bound(groups[g]), Lh = ball_lower_bound(groups[h2]);
+                                if (Lg * Lg + Lh * Lh < now) {
+                                    // every iterate's radius is an upper bound of the optimum: 40 steps screen, 400 decide
+                                    const double Sg = ball_of(groups[g], cen, 40), Sh = ball_of(groups[h2], cen, 40);
+                                    if (Sg * Sg + Sh * Sh < now * 1.1) {
+                                        const double Rg = ball_of(groups[g], cen), Rh = ball_of(groups[h2], cen);
+                                        if (Rg * Rg + Rh * Rh < now) { R2[g] = Rg * Rg; R2[h2] = Rh * Rh; improved = true; better = true; }
+                                    }
+                                }
+                                if (!better) std::swap(groups[g][a], groups[h2][b2]);
                             }
                 if (!improved) break;
             }
@@ -935,11 +967,11 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         auto sgroups = make_groups(stat_ids), mgroups = make_groups(mov_ids);
         refine_groups(sgroups);
         refine_groups(mgroups);
-        std::vector<float4> sph, big, mov, rect;
+        std::vector<float4> sph, big, mov, rect, bounds;
         std::vector<uint32_t> ids;
         const float4 dummy = make_float4(0.f, 0.f, 0.f, -1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (const auto &g : sgroups) {
-            sph.push_back(bound_of(g));
+            bounds.push_back(bound_of(g));
             for (int k = 0; k < 4; ++k) {
                 if (k < (int)g.size()) {
                     const DevPrim &d = flat[g[k]];
@@ -955,7 +987,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         }
         while (ids.size() & 3) ids.push_back(0);
         for (const auto &g : mgroups) {
-            mov.push_back(bound_of(g));
+            bounds.push_back(bound_of(g));
             for (int k = 0; k < 4; ++k) {
                 if (k < (int)g.size()) {
                     const DevPrim &d = flat[g[k]];
@@ -1018,7 +1050,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                         if (f >= 0 && !(mask & (1u << f))) { mask |= 1u << f; ids6[f] = r3; }
                     }
                     if (__builtin_popcount(mask) < 3) continue;
-                    for (int f = 0; f < 6; ++f) if (mask & (1u << f)) boxed[ids6[f]] = 1; else ids6[f] = 0;
+                    for (int f = 0; f < 6; ++f) if (mask & (1u << f)) boxed[ids6[f]] = 1; else ids6[f] = kMiss;  // absent face: id -1 never wins
                     const int slot = s->prims[a].xform >= 0 ? xform_slot_of(s->prims[a].xform) : -1;
                     boxes4.push_back(make_float4((float)c.x0, (float)c.x1, (float)c.y0, (float)c.y1));
                     boxes4.push_back(make_float4((float)c.z0, (float)c.z1, bits_to_float((uint32_t)(slot + 1)), bits_to_float(mask)));
@@ -1070,7 +1102,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                 have_prev = true;
             }
         }
-        fl.n_sphere_real = (uint32_t)(stat_ids.size() + big_ids.size() + mov_ids.size());
+        fl.flags = sgroups.size() + mgroups.size() < 3 ? kFlatNoBounds : 0u;
         fl.n_sph_groups = (uint32_t)sgroups.size(); fl.n_big = (uint32_t)big_ids.size();
         fl.n_mov_groups = (uint32_t)mgroups.size(); fl.n_rect = (uint32_t)rect_ids.size();
         fl.off_sph = 0;
@@ -1081,13 +1113,16 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         fl.n_runs = (uint32_t)runs.size();
         fl.off_boxes = fl.off_runs + (uint32_t)runs.size();
         fl.n_boxes = (uint32_t)(boxes4.size() / kBoxF4);
-        fl.off_ids = fl.off_boxes + (uint32_t)boxes4.size();
+        while (bounds.size() & 3) bounds.push_back(make_float4(0.f, 0.f, 0.f, NAN));  // the scan tests bounds four at a time
+        fl.off_bounds = fl.off_boxes + (uint32_t)boxes4.size();
+        fl.off_ids = fl.off_bounds + (uint32_t)bounds.size();
         blob.insert(blob.end(), sph.begin(), sph.end());
         blob.insert(blob.end(), big.begin(), big.end());
         blob.insert(blob.end(), mov.begin(), mov.end());
         blob.insert(blob.end(), rect.begin(), rect.end());
         blob.insert(blob.end(), runs.begin(), runs.end());
         blob.insert(blob.end(), boxes4.begin(), boxes4.end());
+        blob.insert(blob.end(), bounds.begin(), bounds.end());
         const size_t at = blob.size();
         blob.resize(at + ids.size() / 4);
         if (!ids.empty()) std::memcpy(&blob[at], ids.data(), ids.size() * 4);

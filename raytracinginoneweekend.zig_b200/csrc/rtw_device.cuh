@@ -77,9 +77,11 @@ struct DevPerlin {
 // Shared-memory image of a small scene for the flat scan, as one blob of float4 (offsets in float4
 // units).  Primitives are SEGMENTED BY KIND and small spheres are packed into spatial GROUPS of four
 // behind a bounding sphere, so that a whole warp can skip a group with one vote:
-//   sph groups : 5 x float4  = bound (cx, cy, cz, R) + 4 members (cx, cy, cz, r^2)
+//   bounds     : 1 x float4 per group, static groups then moving groups: (cx, cy, cz, R), the smallest ball enclosing the
+//                members over the shutter interval; padded to a multiple of four with NaN radii (never pass)
+//   sph groups : 4 x float4  = 4 members (cx, cy, cz, r^2)
 //   big        : 1 x float4  (cx, cy, cz, r^2) per big static sphere; DevBigSphere i in scene.bigs
-//   mov groups : 9 x float4  = bound + 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}
+//   mov groups : 8 x float4  = 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}
 //   rect       : 2 x float4 per rect: (a0, a1, b0, b1), (k, bits(prim id), -, -), sorted into RUNS of equal
 //                (instance transform, orientation) so the object-space ray is set up once per run and the
 //                inner loop is specialised per orientation and branch-free
@@ -95,12 +97,13 @@ struct DevPerlin {
 // Unused member slots have r^2 = -1 (never hit).
 constexpr uint32_t kRunSameXform = 0x80000000u;
 constexpr uint32_t kBoxF4 = 5;
+constexpr uint32_t kFlatNoBounds = 1u;  // fewer than three sphere groups: the scan tests their members without the bounds
 struct FlatLayout {
     uint32_t n_sph_groups, n_big, n_mov_groups, n_rect;
     uint32_t off_sph, off_big, off_mov, off_rect, off_ids;
     uint32_t total_f4;
-    uint32_t n_sphere_real;  // for the event counters
-    uint32_t n_runs, off_runs, n_boxes, off_boxes, pad2;
+    uint32_t flags;          // kFlatNoBounds
+    uint32_t n_runs, off_runs, n_boxes, off_boxes, off_bounds;
 };
 
 struct DevScene {

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
                 pool_next += take;
             }
             // ---- start the traversal of every lane that has a ray and is not traversing ----
-            if (alive && !trav) trav = !tv.init(r, sc);
+            if (alive && !trav) trav = !tv.init(r, sc, 0.001f);
             if (!__any_sync(0xffffffffu, alive)) break;  // pool exhausted and every path finished
         }
         // ---- leaf phase: lanes parked at a leaf wait until enough of them have gathered (or nobody is
@@ -383,13 +383,13 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
             const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
             const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
             if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
-                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS>(r, sc, 0.001f, stack, cn);
+                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS>(r, sc, stack, cn);
             }
         }
         // ---- interior phase ----
 #pragma unroll 1
         for (uint32_t k = 0; k < rp.steps_per_round; ++k) {
-            if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, 0.001f, stack, cn);
+            if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, stack, cn);
         }
     }
     if (STATS) cn.flush(rp.stats);
@@ -489,8 +489,9 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     }
     Counters<false> cn;
     Hit h{0.0f, kMiss};
-    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, active, s_flat, sc.flat, sc, 0.001f, cn);
-    else if (active) h = closest_hit_bvh<false>(r, sc, 0.001f, cn);
+    float rl = 1.0f;  // 1/|d|: the searches work with the unit direction and return distances
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, active, s_flat, sc.flat, sc, 0.001f, cn, &rl);
+    else if (active) h = closest_hit_bvh<false>(r, sc, 0.001f, cn, &rl);
     if (!active) return;
     if (h.slot == kMiss) {
         prim_id[idx] = kMiss; t_out[idx] = 0.0f;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     if (VARIANT == VAR_FLAT) { id = h.slot; prim = sc.prims_flat[id]; }
     else { prim = sc.prims_bvh[h.slot]; id = sc.bvh_prim_id[h.slot]; }
     const Surface s = finalise_hit<false>(r, prim, h.t, sc, cn);
-    prim_id[idx] = id; t_out[idx] = h.t;
+    prim_id[idx] = id; t_out[idx] = h.t * rl;  // the reference's parameter t = s / |d|
     normal[3 * idx] = s.nx; normal[3 * idx + 1] = s.ny; normal[3 * idx + 2] = s.nz;
     if (uv) {
         float u = __fdividef(s.u, s.ru), v = __fdividef(s.v, s.rv);  // rect: numerator / denominator (lazy division)

@@ -61,9 +61,22 @@ struct Ray {
 };
 
 struct Hit {
-    float t;
+    float t;        // distance along the UNIT direction (see normalise_ray), not the reference's parameter
     uint32_t slot;  // index into the prim array that was searched; kMiss = no hit
 };
+
+// Rays are TRACED AND SHADED with a unit direction u = d/|d| and distances s = t |d|.  The reference leaves d
+// un-normalised (main.zig:94, material.zig:45-48) and its t_min = 0.001 is in units of THAT parameter (SURVEY App. B
+// Q18), so the closest-hit searches normalise the ray in place when they start and scale t_min by |d|; with u.u = 1 the
+// quadratic's `a` drops out of every sphere and bound test, and Vec3.normalized (vec.zig:33-40) out of metal and dielectric
+// scattering.  Hit points are o + s u = o + t d.  Only the probes convert back (t = s * rl) for comparison with the oracle.
+// Returns |d|; rl = 1/|d| (MUFU.RSQ, ~2 ulp: |u|^2 = 1 +- 3e-7, covered by the slack of every culling test).
+__device__ __forceinline__ float normalise_ray(Ray &r, float &rl) {
+    const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(add));
+    r.dx *= rl; r.dy *= rl; r.dz *= rl;
+    return add * rl;
+}
 
 template <bool STATS>
 struct Counters {
@@ -90,55 +103,60 @@ struct Counters<true> {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Primitive tests.  `inv_a` = 1/(d.d), `add` = d.d of the (un-normalised, main.zig:94) direction.
-// Accept rule = the reference's: nearest root in [t_min, t_max], both ends inclusive
-// (hittable.zig:106-116).
+// Primitive tests on a unit-direction ray `u`; distances s in [s_min, s_max].
+// Accept rule = the reference's: nearest root in the range, both ends inclusive (hittable.zig:106-116).
 // ---------------------------------------------------------------------------------------------
 // Sphere: numerically robust fp32 form.  The textbook b^2 - a*c of hittable.zig:96-101 cancels
 // catastrophically in fp32 for small far spheres (measured: -0.5 % image bias from false
 // self-intersections); instead the discriminant comes from the perpendicular offset l of the
-// centre from the ray line (disc' = r^2 - |l|^2), and the roots from q = b' + sign(b') sqrt(a disc'),
-// t = {c/q, q/a}.  Same roots in exact arithmetic.
-template <bool STATS>
-__device__ __forceinline__ bool sphere_test(const Ray &r, float add, float inv_a, const DevPrim &p,
-                                            const DevBigSphere *bigs, float t_min, float t_max, float &t_out,
-                                            Counters<STATS> &cn) {
-    cn.add(ST_SPHERE_TESTS);
-    const float cx = fmaf(p.b.x, r.time, p.a.x), cy = fmaf(p.b.y, r.time, p.a.y), cz = fmaf(p.b.z, r.time, p.a.z);
-    const float ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
-    const float bp = fmaf(ocx, r.dx, fmaf(ocy, r.dy, ocz * r.dz));
-    const float k = bp * inv_a;
-    const float lx = fmaf(-k, r.dx, ocx), ly = fmaf(-k, r.dy, ocy), lz = fmaf(-k, r.dz, ocz);
-    const float rr = p.a.w * p.a.w;
-    const float discp = fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, rr)));
-    if (discp < 0.0f) return false;
-    cn.add(ST_SPHERE_ROOTS);
-    float c;
-    const uint32_t big = (__float_as_uint(p.b.w) >> 8) & 0xFFFu;
-    if (big) {
-        // |o-c|^2 - r^2 about a reference point q on the surface: no 1e6 - 1e6 cancellation for the
-        // r=1000 ground sphere of main.zig:172.
-        const DevBigSphere g = bigs[big - 1];
-        const float ax = r.ox - g.qx, ay = r.oy - g.qy, az = r.oz - g.qz;
-        const float aa = fmaf(ax, ax, fmaf(ay, ay, az * az));
-        const float am = fmaf(ax, g.mx, fmaf(ay, g.my, az * g.mz));
-        c = fmaf(2.0f, am, aa) + g.K;
-    } else {
-        c = fmaf(ocx, ocx, fmaf(ocy, ocy, fmaf(ocz, ocz, -rr)));
-    }
-    const float sq = sqrt_approx(add * discp);
+// centre from the ray line (disc' = r^2 - |l|^2), and the roots from q = b' + sign(b') sqrt(disc'),
+// s = {c/q, q}.  Same roots in exact arithmetic.
+// discriminant of the robust form: returns disc', writes oc and b' = oc.u
+__device__ __forceinline__ float sphere_disc(const Ray &u, float cx, float cy, float cz, float rr,
+                                             float &ocx, float &ocy, float &ocz, float &bp) {
+    ocx = u.ox - cx; ocy = u.oy - cy; ocz = u.oz - cz;
+    bp = fmaf(ocx, u.dx, fmaf(ocy, u.dy, ocz * u.dz));
+    const float lx = fmaf(-bp, u.dx, ocx), ly = fmaf(-bp, u.dy, ocy), lz = fmaf(-bp, u.dz, ocz);
+    return fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, rr)));
+}
+// roots from (c, b', disc'): nearest root in [s_min, s_max]
+__device__ __forceinline__ bool sphere_root(float c, float bp, float discp, float s_min, float s_max, float &s_out) {
+    const float sq = sqrt_approx(discp);
     const float bq = -bp;
     const float q = bq + copysignf(sq, bq);
-    const float t0 = c * rcp_approx(q), t1 = q * inv_a;
-    const float lo = fminf(t0, t1), hi = fmaxf(t0, t1);
-    float root = lo;
-    if (root < t_min || t_max < root) {
-        root = hi;
-        if (root < t_min || t_max < root) return false;
+    const float t0 = c * rcp_approx(q), t1 = q;
+    float root = fminf(t0, t1);
+    if (root < s_min || s_max < root) {
+        root = fmaxf(t0, t1);
+        if (root < s_min || s_max < root) return false;
     }
-    if (!(root == root)) return false;  // q == 0 (ray through the centre of a zero-disc sphere)
-    t_out = root;
+    if (!(root == root)) return false;  // q == 0 (ray through the centre of a zero-disc sphere), NaN disc'
+    s_out = root;
     return true;
+}
+// |o - centre|^2 - r^2 of a big sphere about a reference point q on its surface: no 1e6 - 1e6 cancellation for the
+// r = 1000 ground sphere of main.zig:172
+__device__ __forceinline__ float big_sphere_c(const Ray &u, const DevBigSphere &g) {
+    const float ax = u.ox - g.qx, ay = u.oy - g.qy, az = u.oz - g.qz;
+    const float aa = fmaf(ax, ax, fmaf(ay, ay, az * az));
+    const float am = fmaf(ax, g.mx, fmaf(ay, g.my, az * g.mz));
+    return fmaf(2.0f, am, aa) + g.K;
+}
+// the BVH leaves' sphere test: the same operations in the same order as the flat scan's member tests, so both searches
+// return bit-identical distances
+template <bool STATS>
+__device__ __forceinline__ bool sphere_test(const Ray &u, const DevPrim &p, const DevBigSphere *bigs, float s_min, float s_max,
+                                            float &s_out, Counters<STATS> &cn) {
+    cn.add(ST_SPHERE_TESTS);
+    const float cx = fmaf(p.b.x, u.time, p.a.x), cy = fmaf(p.b.y, u.time, p.a.y), cz = fmaf(p.b.z, u.time, p.a.z);
+    const float rr = p.a.w * p.a.w;
+    float ocx, ocy, ocz, bp;
+    const float discp = sphere_disc(u, cx, cy, cz, rr, ocx, ocy, ocz, bp);
+    if (!(discp >= 0.0f)) return false;
+    cn.add(ST_SPHERE_ROOTS);
+    const uint32_t big = (__float_as_uint(p.b.w) >> 8) & 0xFFFu;
+    const float c = big ? big_sphere_c(u, bigs[big - 1]) : fmaf(ocx, ocx, fmaf(ocy, ocy, fmaf(ocz, ocz, -rr)));
+    return sphere_root(c, bp, discp, s_min, s_max, s_out);
 }
 
 // Axis-aligned rect in its object space.  kind: PK_XY (k on z), PK_XZ (k on y), PK_YZ (k on x).
@@ -178,12 +196,11 @@ __device__ __forceinline__ bool rect_test(const Ray &r, const DevPrim &p, uint32
 }
 
 template <bool STATS>
-__device__ __forceinline__ bool prim_test(const Ray &r, float add, float inv_a, const DevPrim &p,
-                                          const DevScene &sc, float t_min, float t_max, float &t_out,
-                                          Counters<STATS> &cn) {
+__device__ __forceinline__ bool prim_test(const Ray &u, const DevPrim &p, const DevScene &sc, float s_min, float s_max,
+                                          float &s_out, Counters<STATS> &cn) {
     const uint32_t kind = __float_as_uint(p.b.w) & 0xFFu;
-    if (kind == PK_SPHERE) return sphere_test<STATS>(r, add, inv_a, p, sc.bigs, t_min, t_max, t_out, cn);
-    return rect_test<STATS>(r, p, kind, sc.xforms, t_min, t_max, t_out, cn);
+    if (kind == PK_SPHERE) return sphere_test<STATS>(u, p, sc.bigs, s_min, s_max, s_out, cn);
+    return rect_test<STATS>(u, p, kind, sc.xforms, s_min, s_max, s_out, cn);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,72 +228,64 @@ __device__ __forceinline__ void flat_consider(FlatBest &b, float t, uint32_t id)
     if (flat_better(b, t, id)) { b.t = t; b.id = id; }
 }
 
-// discriminant of the robust form (see sphere_test): returns disc', writes oc and bp
-__device__ __forceinline__ float sphere_disc(const Ray &r, float inv_a, float cx, float cy, float cz, float rr,
-                                             float &ocx, float &ocy, float &ocz, float &bp) {
-    ocx = r.ox - cx; ocy = r.oy - cy; ocz = r.oz - cz;
-    bp = fmaf(ocx, r.dx, fmaf(ocy, r.dy, ocz * r.dz));
-    const float k = bp * inv_a;
-    const float lx = fmaf(-k, r.dx, ocx), ly = fmaf(-k, r.dy, ocy), lz = fmaf(-k, r.dz, ocz);
-    return fmaf(-lx, lx, fmaf(-ly, ly, fmaf(-lz, lz, rr)));
-}
-// roots from (c, b', disc'): nearest root in [t_min, t_max]
-__device__ __forceinline__ bool sphere_root(float add, float inv_a, float c, float bp, float discp, float t_min,
-                                            float t_max, float &t_out) {
-    const float sq = sqrt_approx(add * discp);
-    const float bq = -bp;
-    const float q = bq + copysignf(sq, bq);
-    const float t0 = c * rcp_approx(q), t1 = q * inv_a;
-    float root = fminf(t0, t1);
-    if (root < t_min || t_max < root) {
-        root = fmaxf(t0, t1);
-        if (root < t_min || t_max < root) return false;
-    }
-    if (!(root == root)) return false;
-    t_out = root;
-    return true;
-}
-
-// does the ray (t >= 0) possibly touch the bounding sphere?  line test + "entirely behind" test
-// `reach` = best.t * |d|: the bound is also skipped when even its nearest point lies beyond the current
-// closest hit (the big spheres — the ground — are tested first so that this culls)
+// does the ray (s >= 0) possibly touch the bounding sphere?  line test + "entirely behind" test
+// `reach` = distance of the current closest hit: the bound is also skipped when even its nearest point lies beyond it
+// (the big spheres — the ground — are tested first so that this culls)
 // b = (centre, R): the radius itself is stored (R^2 is one multiply away, R would be a MUFU)
-// This is a CULLING test, so it uses the cheap form |oc|^2 a - (oc.d)^2 <= a R^2 (a = d.d) instead of the
-// cancellation-free perpendicular offset the member tests need, and pays for the fp32 cancellation with slack:
-// the left side carries an absolute error below 12 * 2^-24 * |oc|^2 a (three-term dot products, one FMA rounding),
-// so the bound is kept whenever lhs <= a (R^2 + 2e-6 |oc|^2).  False positives only cost time.
-__device__ __forceinline__ bool bound_hit(const Ray &r, float add, const float4 b, float reach) {
-    const float ox = r.ox - b.x, oy = r.oy - b.y, oz = r.oz - b.z;
+// This is a CULLING test, so it uses the cheap form |oc|^2 - (oc.u)^2 <= R^2 instead of the cancellation-free
+// perpendicular offset the member tests need, and pays for the fp32 cancellation with slack: the left side carries an
+// absolute error below 16 * 2^-24 * |oc|^2 (three-term dot products, one FMA rounding, |u|^2 = 1 +- 3e-7), so the bound
+// is kept whenever lhs <= R^2 + 2e-6 |oc|^2.  False positives only cost time.
+__device__ __forceinline__ bool bound_hit(const Ray &u, const float4 b, float reach) {
+    const float ox = u.ox - b.x, oy = u.oy - b.y, oz = u.oz - b.z;
     const float rr = b.w * b.w;
     const float oo = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
-    const float bp = fmaf(ox, r.dx, fmaf(oy, r.dy, oz * r.dz));
-    const float lhs = fmaf(-bp, bp, oo * add);
-    const float rhs = fmaf(oo, 2e-6f, rr) * add;
+    const float bp = fmaf(ox, u.dx, fmaf(oy, u.dy, oz * u.dz));
+    const float lhs = fmaf(-bp, bp, oo);
+    const float rhs = fmaf(oo, 2e-6f, rr);
     // origin outside the bound and either the bound is behind, or |oc| - R > reach, i.e. |oc|^2 > (reach + R)^2
-    const float lim = fmaf(reach, fmaf(2.0f, b.w, reach), rr);
+    const float far = reach + b.w, lim = far * far;
     // bitwise, not short-circuit: the test stays one straight line of predicate logic (lim >= rr, so oo > lim implies
-    // the origin is outside)
+    // the origin is outside).  A NaN radius (padding entries of the bounds array) fails lhs <= rhs.
     return (lhs <= rhs) & !((oo > lim) | ((oo > rr) & (bp > 0.0f)));
+}
+// the same test, OR-ing `bit` into `mask` when it passes: four chained FSETP and one predicated LOP3 (left to itself
+// the compiler materialises the predicates with three SEL per bound)
+__device__ __forceinline__ void bound_hit_into(const Ray &u, const float4 b, float reach, uint32_t &mask, uint32_t bit) {
+    const float ox = u.ox - b.x, oy = u.oy - b.y, oz = u.oz - b.z;
+    const float rr = b.w * b.w;
+    const float oo = fmaf(ox, ox, fmaf(oy, oy, oz * oz));
+    const float bp = fmaf(ox, u.dx, fmaf(oy, u.dy, oz * u.dz));
+    const float lhs = fmaf(-bp, bp, oo);
+    const float rhs = fmaf(oo, 2e-6f, rr);
+    const float far = reach + b.w, lim = far * far;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, 0f00000000;\n\t"
+        "setp.gt.and.f32 p, %2, %3, p;\n\t"
+        "setp.gt.or.f32 p, %2, %4, p;\n\t"
+        "setp.le.and.f32 p, %5, %6, !p;\n\t"
+        "@p or.b32 %0, %0, %7;\n\t}"
+        : "+r"(mask) : "f"(bp), "f"(oo), "f"(rr), "f"(lim), "f"(lhs), "f"(rhs), "r"(bit));
 }
 
 template <bool STATS>
-__device__ __forceinline__ void flat_static_pair(const Ray &r, float add, float inv_a, const float4 a0, const float4 a1,
-                                                 uint32_t id0, uint32_t id1, bool active, float t_min, FlatBest &best,
+__device__ __forceinline__ void flat_static_pair(const Ray &u, const float4 a0, const float4 a1,
+                                                 uint32_t id0, uint32_t id1, bool active, float s_min, FlatBest &best,
                                                  Counters<STATS> &cn) {
     float o0x, o0y, o0z, b0, o1x, o1y, o1z, b1;
-    const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, o0x, o0y, o0z, b0);
-    const float d1 = sphere_disc(r, inv_a, a1.x, a1.y, a1.z, a1.w, o1x, o1y, o1z, b1);
+    const float d0 = sphere_disc(u, a0.x, a0.y, a0.z, a0.w, o0x, o0y, o0z, b0);
+    const float d1 = sphere_disc(u, a1.x, a1.y, a1.z, a1.w, o1x, o1y, o1z, b1);
     if (active && d0 >= 0.0f) {
         cn.add(ST_SPHERE_ROOTS);
         const float c = fmaf(o0x, o0x, fmaf(o0y, o0y, fmaf(o0z, o0z, -a0.w)));
         float t;
-        if (sphere_root(add, inv_a, c, b0, d0, t_min, best.t, t)) flat_consider(best, t, id0);
+        if (sphere_root(c, b0, d0, s_min, best.t, t)) flat_consider(best, t, id0);
     }
     if (active && d1 >= 0.0f) {
         cn.add(ST_SPHERE_ROOTS);
         const float c = fmaf(o1x, o1x, fmaf(o1y, o1y, fmaf(o1z, o1z, -a1.w)));
         float t;
-        if (sphere_root(add, inv_a, c, b1, d1, t_min, best.t, t)) flat_consider(best, t, id1);
+        if (sphere_root(c, b1, d1, s_min, best.t, t)) flat_consider(best, t, id1);
     }
 }
 
@@ -302,27 +311,15 @@ __device__ __forceinline__ void rect_run(float ok, float dk, float oa, float da,
     }
 }
 
-// One face of a box: the plane is crossed at t; the ray is inside the two OTHER slabs exactly while t is in [lo, hi]
-// (their entry/exit parameters), which is the in-plane bounds test of XyRect/XzRect/YzRect.hit (hittable.zig:283-287) with
-// the inequalities moved from positions to parameters: x0 <= o + t d <= x1  <=>  lo_x <= t <= hi_x.  Both ends inclusive
-// like the reference's; equal t goes to the larger prim id (its list order).  The parameters two faces compare are the SAME
-// floats, so at a shared edge at least one of them accepts: a box is watertight by construction.
+// `r` comes in with any direction and leaves with the unit direction (normalise_ray); the returned Hit::t is the distance
+// along it.  `rl_out` (optional) receives 1/|d| for callers that report the reference's parameter t = s / |d|.
 template <bool STATS>
-__device__ __forceinline__ void box_face(float t, float lo, float hi, bool present, uint32_t id, float t_min, FlatBest &best,
-                                         Counters<STATS> &cn) {
-    const bool hit = present & (t >= t_min) & (t <= best.t) & (t >= lo) & (t <= hi);
-    if (STATS) { if (hit) cn.add(ST_RECT_ACCEPTS); }
-    const bool take = hit && flat_better(best, t, id);
-    best.t = take ? t : best.t;
-    best.id = take ? id : best.id;
-}
-
-template <bool STATS>
-__device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const float4 *s, const FlatLayout &L,
-                                                const DevScene &sc, float t_min, Counters<STATS> &cn) {
-    const float add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-    const float inv_a = rcp_approx(add);
-    const float len = sqrt_approx(add) * 1.00001f;  // |d|, rounded up: best.t * len = reach of the current closest hit
+__device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float4 *s, const FlatLayout &L,
+                                                const DevScene &sc, float t_min, Counters<STATS> &cn, float *rl_out = nullptr) {
+    float rl;
+    t_min *= normalise_ray(r, rl);  // s_min = t_min |d|
+    if (rl_out) *rl_out = rl;
+    const Ray &u = r;
     // inactive lanes scan with reach 0: a bound then passes only if their (stale) origin lies inside it, so they
     // practically never keep a group alive in the votes below and the votes need no `active` term
     FlatBest best{active ? __int_as_float(0x7f800000) : 0.0f, kMiss};
@@ -334,50 +331,61 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
         for (uint32_t i = 0; i < L.n_big; ++i) {
             const float4 a0 = sp[i];
             float ox, oy, oz, bp;
-            const float d0 = sphere_disc(r, inv_a, a0.x, a0.y, a0.z, a0.w, ox, oy, oz, bp);
+            const float d0 = sphere_disc(u, a0.x, a0.y, a0.z, a0.w, ox, oy, oz, bp);
             if (active) cn.add(ST_SPHERE_TESTS);
             if (active && d0 >= 0.0f) {
                 cn.add(ST_SPHERE_ROOTS);
-                const DevBigSphere g = sc.bigs[i];
-                const float ax = r.ox - g.qx, ay = r.oy - g.qy, az = r.oz - g.qz;
-                const float aa = fmaf(ax, ax, fmaf(ay, ay, az * az));
-                const float am = fmaf(ax, g.mx, fmaf(ay, g.my, az * g.mz));
-                const float c = fmaf(2.0f, am, aa) + g.K;
+                const float c = big_sphere_c(u, sc.bigs[i]);
                 float t;
-                if (sphere_root(add, inv_a, c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[4 * L.n_sph_groups + i]);
+                if (sphere_root(c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[4 * L.n_sph_groups + i]);
             }
         }
     }
-    // ---- static sphere groups ----
+    // ---- sphere groups, static then moving, FOUR AT A TIME: the four bounds as straight-line code, each lane collecting
+    //      its own pass bits; ONE warp reduction (REDUX.OR) turns them into the set of groups somebody needs; then only those
+    //      groups' members are tested, by every lane.  Against a vote and a branch per group this is 8 fewer instructions
+    //      per bound; the reach (distance of the closest hit so far) is refreshed between chunks.  Scenes with fewer than
+    //      three groups skip the bounds (L.flags & kFlatNoBounds): the test costs what it saves there ----
     {
-        const float4 *gp = s + L.off_sph, *const ge = gp + 5 * L.n_sph_groups;
-        const uint32_t *ip = ids;
+        const uint32_t ng = L.n_sph_groups + L.n_mov_groups;
+        const float4 *bnd = s + L.off_bounds;  // padded to a multiple of four with NaN radii (never pass)
+        const float4 *sph = s + L.off_sph, *mov = s + L.off_mov;
+        const uint32_t mov_ids = 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u);
 #pragma unroll 1
-        for (; gp < ge; gp += 5, ip += 4) {
-            if (active) cn.add(ST_SPHERE_TESTS);  // the bound is a sphere test too
-            if (!__any_sync(0xffffffffu, bound_hit(r, add, gp[0], best.t * len))) continue;
-            if (active) cn.add(ST_SPHERE_TESTS, 4);
-            const uint4 id = *reinterpret_cast<const uint4 *>(ip);
-            flat_static_pair<STATS>(r, add, inv_a, gp[1], gp[2], id.x, id.y, active, t_min, best, cn);
-            flat_static_pair<STATS>(r, add, inv_a, gp[3], gp[4], id.z, id.w, active, t_min, best, cn);
-        }
-    }
-    // ---- moving sphere groups: centre(time) = cb + vel*time (hittable.zig:219-221) ----
-    {
-        const float4 *gp = s + L.off_mov, *const ge = gp + 9 * L.n_mov_groups;
-        const uint32_t *ip = ids + 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u);
-#pragma unroll 1
-        for (; gp < ge; gp += 9, ip += 4) {
-            if (active) cn.add(ST_SPHERE_TESTS);
-            if (!__any_sync(0xffffffffu, bound_hit(r, add, gp[0], best.t * len))) continue;
-            if (active) { cn.add(ST_SPHERE_TESTS, 4); cn.add(ST_MOVING_TESTS, 4); }
-            const uint4 id = *reinterpret_cast<const uint4 *>(ip);
+        for (uint32_t base = 0; base < ng; base += 4u, bnd += 4) {
+            const uint32_t nb = min(4u, ng - base);
+            uint32_t m = (1u << nb) - 1u;
+            if (!(L.flags & kFlatNoBounds)) {
+                if (active) cn.add(ST_SPHERE_TESTS, nb);  // the bound is a sphere test too
+                const float reach = best.t;
+                m = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4 a0 = gp[1 + 4 * h], v0 = gp[2 + 4 * h], a1 = gp[3 + 4 * h], v1 = gp[4 + 4 * h];
-                const float4 c0 = make_float4(fmaf(v0.x, r.time, a0.x), fmaf(v0.y, r.time, a0.y), fmaf(v0.z, r.time, a0.z), a0.w);
-                const float4 c1 = make_float4(fmaf(v1.x, r.time, a1.x), fmaf(v1.y, r.time, a1.y), fmaf(v1.z, r.time, a1.z), a1.w);
-                flat_static_pair<STATS>(r, add, inv_a, c0, c1, h ? id.z : id.x, h ? id.w : id.y, active, t_min, best, cn);
+                for (int k = 0; k < 4; ++k) bound_hit_into(u, bnd[k], reach, m, 1u << k);
+                m = __reduce_or_sync(0xffffffffu, m);
+            }
+#pragma unroll 1
+            while (m) {
+                const uint32_t g = base + (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                if (active) cn.add(ST_SPHERE_TESTS, 4);
+                if (g < L.n_sph_groups) {
+                    const float4 *gp = sph + 4 * g;
+                    const uint4 id = *reinterpret_cast<const uint4 *>(ids + 4 * g);
+                    flat_static_pair<STATS>(u, gp[0], gp[1], id.x, id.y, active, t_min, best, cn);
+                    flat_static_pair<STATS>(u, gp[2], gp[3], id.z, id.w, active, t_min, best, cn);
+                } else {  // centre(time) = cb + vel*time (hittable.zig:219-221)
+                    const uint32_t gm = g - L.n_sph_groups;
+                    const float4 *gp = mov + 8 * gm;
+                    const uint4 id = *reinterpret_cast<const uint4 *>(ids + mov_ids + 4 * gm);
+                    if (active) cn.add(ST_MOVING_TESTS, 4);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a0 = gp[4 * h], v0 = gp[1 + 4 * h], a1 = gp[2 + 4 * h], v1 = gp[3 + 4 * h];
+                        const float4 c0 = make_float4(fmaf(v0.x, u.time, a0.x), fmaf(v0.y, u.time, a0.y), fmaf(v0.z, u.time, a0.z), a0.w);
+                        const float4 c1 = make_float4(fmaf(v1.x, u.time, a1.x), fmaf(v1.y, u.time, a1.y), fmaf(v1.z, u.time, a1.z), a1.w);
+                        flat_static_pair<STATS>(u, c0, c1, h ? id.z : id.x, h ? id.w : id.y, active, t_min, best, cn);
+                    }
+                }
             }
         }
     }
@@ -390,13 +398,13 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
             const uint4 I0 = *reinterpret_cast<const uint4 *>(bx + 2);
             const float4 X = bx[3], T = bx[4];  // (id4, id5, cos, sin), (tx, ty, tz, -)
             const uint2 I1 = make_uint2(__float_as_uint(X.x), __float_as_uint(X.y));
-            const uint32_t xf = __float_as_uint(B.z), mask = __float_as_uint(B.w);
-            float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+            const uint32_t xf = __float_as_uint(B.z), mask = __float_as_uint(B.w);  // mask: which faces exist (event counters only)
+            float ox = u.ox, oy = u.oy, oz = u.oz, dx = u.dx, dy = u.dy, dz = u.dz;
             if (xf) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573); the composed chain
                        // sits in the record itself (same floats as DevScene::xforms[xf - 1], which finalise_hit reads)
                 if (active) cn.add(ST_XFORM_APPS);
-                ox = fmaf(X.z, r.ox, -X.w * r.oz) + T.x; oy = r.oy + T.y; oz = fmaf(X.w, r.ox, X.z * r.oz) + T.z;
-                dx = fmaf(X.z, r.dx, -X.w * r.dz); dz = fmaf(X.w, r.dx, X.z * r.dz);
+                ox = fmaf(X.z, u.ox, -X.w * u.oz) + T.x; oy = u.oy + T.y; oz = fmaf(X.w, u.ox, X.z * u.oz) + T.z;
+                dx = fmaf(X.z, u.dx, -X.w * u.dz); dz = fmaf(X.w, u.dx, X.z * u.dz);
             }
             if (active) cn.add(ST_RECT_TESTS, __popc(mask));
             const float ix = rcp_approx(dx), iy = rcp_approx(dy), iz = rcp_approx(dz);
@@ -407,31 +415,46 @@ __device__ __forceinline__ Hit closest_hit_flat(const Ray &r, bool active, const
             const float lox = fminf(tx0, tx1), hix = fmaxf(tx0, tx1);
             const float loy = fminf(ty0, ty1), hiy = fmaxf(ty0, ty1);
             const float loz = fminf(tz0, tz1), hiz = fmaxf(tz0, tz1);
-            const float xlo = fmaxf(loy, loz), xhi = fminf(hiy, hiz);  // inside the y and z slabs: the x faces' bounds
-            const float ylo = fmaxf(lox, loz), yhi = fminf(hix, hiz);
-            const float zlo = fmaxf(lox, loy), zhi = fminf(hix, hiy);
-            box_face<STATS>(tz1, zlo, zhi, active && (mask & 1u), I0.x, t_min, best, cn);
-            box_face<STATS>(tz0, zlo, zhi, active && (mask & 2u), I0.y, t_min, best, cn);
-            box_face<STATS>(ty1, ylo, yhi, active && (mask & 4u), I0.z, t_min, best, cn);
-            box_face<STATS>(ty0, ylo, yhi, active && (mask & 8u), I0.w, t_min, best, cn);
-            box_face<STATS>(tx1, xlo, xhi, active && (mask & 16u), I1.x, t_min, best, cn);
-            box_face<STATS>(tx0, xlo, xhi, active && (mask & 32u), I1.y, t_min, best, cn);
+            // A face's in-plane bounds test (hittable.zig:283-287) in parameters: the NEAR face of axis a (at t = lo_a) is
+            // hit iff lo_a >= the other two lows and <= the other two highs, i.e. (lo_a <= hi_a always) iff
+            // lo_a == t_en = max(lows) and t_en <= t_ex = min(highs); the FAR face iff hi_a == t_ex and t_en <= t_ex.  So of
+            // the six faces only those AT t_en or t_ex can be hit, several of them on an edge or corner, where the list scan
+            // keeps the later element (hittable.zig:235-242) = the largest prim id; absent faces (a room's open side) carry
+            // id -1 and lose every signed comparison.  The box's closest hit is the t_en candidate when it is in range and
+            // present, else the t_ex one: ONE candidate per box meets the running best instead of six.
+            const float t_en = fmaxf(fmaxf(lox, loy), loz), t_ex = fminf(fminf(hix, hiy), hiz);
+            const bool px = tx0 <= tx1, py = ty0 <= ty1, pz = tz0 <= tz1;  // near face = the "0" face of the axis
+            const int32_t nx = (int32_t)(px ? I1.y : I1.x), fx = (int32_t)(px ? I1.x : I1.y);
+            const int32_t ny = (int32_t)(py ? I0.w : I0.z), fy = (int32_t)(py ? I0.z : I0.w);
+            const int32_t nz = (int32_t)(pz ? I0.y : I0.x), fz = (int32_t)(pz ? I0.x : I0.y);
+            const int32_t id_ex = max(max(hix == t_ex ? fx : -1, hiy == t_ex ? fy : -1), hiz == t_ex ? fz : -1);
+            // a ray that only touches an edge or corner (t_en == t_ex) meets near and far faces at the same t
+            const int32_t id_en = max(max(max(lox == t_en ? nx : -1, loy == t_en ? ny : -1), loz == t_en ? nz : -1), t_en == t_ex ? id_ex : -1);
+            const bool cross = active & (t_en <= t_ex);
+            const bool en_ok = cross & (t_en >= t_min) & (t_en <= best.t) & (id_en >= 0);
+            const bool ex_ok = cross & (t_ex >= t_min) & (t_ex <= best.t) & (id_ex >= 0);
+            const float tb = en_ok ? t_en : t_ex;
+            const uint32_t ib = (uint32_t)(en_ok ? id_en : id_ex);
+            if (STATS) { if (en_ok | ex_ok) cn.add(ST_RECT_ACCEPTS); }
+            const bool take = (en_ok | ex_ok) && flat_better(best, tb, ib);
+            best.t = take ? tb : best.t;
+            best.id = take ? ib : best.id;
         }
     }
     // ---- rects: runs of equal (instance transform, orientation); consecutive runs of one instance (a box = three
     //      runs) share the object-space ray, which is therefore set up once per instance, not once per run ----
     {
         const uint4 *runs = reinterpret_cast<const uint4 *>(s + L.off_runs);
-        float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+        float o[3] = {u.ox, u.oy, u.oz}, d[3] = {u.dx, u.dy, u.dz};
         for (uint32_t q = 0; q < L.n_runs; ++q) {
             const uint4 run = runs[q];
             if (!(run.x & kRunSameXform)) {
-                o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; d[0] = r.dx; d[1] = r.dy; d[2] = r.dz;
+                o[0] = u.ox; o[1] = u.oy; o[2] = u.oz; d[0] = u.dx; d[1] = u.dy; d[2] = u.dz;
                 if (run.x) {  // world -> object (Translate.hit + RotateY.hit, hittable.zig:479-483, 560-573)
                     if (active) cn.add(ST_XFORM_APPS);
                     const DevXform x = sc.xforms[run.x - 1u];
-                    o[0] = fmaf(x.c, r.ox, -x.s * r.oz) + x.tx; o[1] = r.oy + x.ty; o[2] = fmaf(x.s, r.ox, x.c * r.oz) + x.tz;
-                    d[0] = fmaf(x.c, r.dx, -x.s * r.dz); d[2] = fmaf(x.s, r.dx, x.c * r.dz);
+                    o[0] = fmaf(x.c, u.ox, -x.s * u.oz) + x.tx; o[1] = u.oy + x.ty; o[2] = fmaf(x.s, u.ox, x.c * u.oz) + x.tz;
+                    d[0] = fmaf(x.c, u.dx, -x.s * u.dz); d[2] = fmaf(x.s, u.dx, x.c * u.dz);
                 }
             }
             const float4 *rp = s + L.off_rect + 2 * run.z;
@@ -472,7 +495,7 @@ constexpr int kBvhStack = 64;
 // current node) followed by at most one leaf visit, so a warp can interleave traversal steps of its
 // lanes with shading/regeneration of the lanes that are done (k_megakernel_bvh).
 struct BvhTraversal {
-    float idx, idy, idz, add, inv_a;
+    float idx, idy, idz, s_min;
     Hit h;
     uint32_t best_id;
     uint32_t cur;  // reference of the node to visit next
@@ -481,10 +504,11 @@ struct BvhTraversal {
     // local memory (ncu r01_m: four LDL and three STL per interior visit); as a separate array only the pushes and
     // pops touch local memory and the scalars above stay in registers.
 
-    // returns true when the traversal is already finished (empty scene)
-    __device__ __forceinline__ bool init(const Ray &r, const DevScene &sc) {
-        add = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-        inv_a = rcp_approx(add);
+    // normalises `r` in place (normalise_ray); returns true when the traversal is already finished (empty scene)
+    __device__ __forceinline__ bool init(Ray &r, const DevScene &sc, float t_min, float *rl_out = nullptr) {
+        float rl;
+        s_min = t_min * normalise_ray(r, rl);
+        if (rl_out) *rl_out = rl;
         idx = rcp_approx(r.dx); idy = rcp_approx(r.dy); idz = rcp_approx(r.dz);
         h = Hit{__int_as_float(0x7f800000), kMiss};
         best_id = 0;
@@ -498,7 +522,7 @@ struct BvhTraversal {
 
     // one interior visit: both children of `cur` (precondition: !at_leaf()).  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
+    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
                                                   Counters<STATS> &cn) {
         const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
         float4 l0, l1, r0, r1;
@@ -508,8 +532,8 @@ struct BvhTraversal {
         const BvhNode R{r0.x, r0.y, r0.z, __float_as_uint(r0.w), r1.x, r1.y, r1.z, __float_as_uint(r1.w)};
         cn.add(ST_NODE_TESTS, 2);
         float tl, tr;
-        const bool hl = slab(L, r, idx, idy, idz, t_min, h.t, tl);
-        const bool hr = slab(R, r, idx, idy, idz, t_min, h.t, tr);
+        const bool hl = slab(L, r, idx, idy, idz, s_min, h.t, tl);
+        const bool hr = slab(R, r, idx, idy, idz, s_min, h.t, tr);
         const uint32_t el = L.a, er = R.a;
         if (hl && hr) {
             const bool left_first = tl <= tr;
@@ -526,7 +550,7 @@ struct BvhTraversal {
 
     // one leaf visit (precondition: at_leaf()): the only primitive-test site.  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
+    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
                                               Counters<STATS> &cn) {
         const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
         for (uint32_t i = 0; i < cnt; ++i) {
@@ -534,7 +558,7 @@ struct BvhTraversal {
             DevPrim p;
             ldg256(sc.prims_bvh + slot, p.a, p.b);
             float t;
-            if (prim_test<STATS>(r, add, inv_a, p, sc, t_min, h.t, t, cn)) {
+            if (prim_test<STATS>(r, p, sc, s_min, h.t, t, cn)) {
                 const uint32_t id = __ldg(sc.bvh_prim_id + slot);
                 if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
             }
@@ -546,20 +570,20 @@ struct BvhTraversal {
 
     // at most one interior visit followed by at most one leaf visit.  Returns true when finished.
     template <bool STATS>
-    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, float t_min, uint32_t (&stack)[kBvhStack],
-                                         Counters<STATS> &cn) {
-        if (!at_leaf() && interior_step<STATS>(r, sc, t_min, stack, cn)) return true;
-        if (at_leaf()) return leaf_step<STATS>(r, sc, t_min, stack, cn);
+    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack], Counters<STATS> &cn) {
+        if (!at_leaf() && interior_step<STATS>(r, sc, stack, cn)) return true;
+        if (at_leaf()) return leaf_step<STATS>(r, sc, stack, cn);
         return false;
     }
 };
 
+// `r` leaves with the unit direction, Hit::t is the distance along it (see closest_hit_flat)
 template <bool STATS>
-__device__ __forceinline__ Hit closest_hit_bvh(const Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn) {
+__device__ __forceinline__ Hit closest_hit_bvh(Ray &r, const DevScene &sc, float t_min, Counters<STATS> &cn, float *rl_out = nullptr) {
     BvhTraversal tv;
     uint32_t stack[kBvhStack];
-    if (tv.init(r, sc)) return tv.h;
-    while (!tv.template step<STATS>(r, sc, t_min, stack, cn)) {}
+    if (tv.init(r, sc, t_min, rl_out)) return tv.h;
+    while (!tv.template step<STATS>(r, sc, stack, cn)) {}
     return tv.h;
 }
 
@@ -799,9 +823,7 @@ __device__ __forceinline__ bool shade_prepare(const DevScene &sc, Ray &r, const 
         beta.x *= a.x; beta.y *= a.y; beta.z *= a.z;
         r.dx = s.nx; r.dy = s.ny; r.dz = s.nz;
     } else {
-        const float dd = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-        const float inv_len = dd > 0.0f ? rsqrtf(dd) : 1.0f;  // Vec3.normalized vec.zig:33-40
-        const float ux = r.dx * inv_len, uy = r.dy * inv_len, uz = r.dz * inv_len;
+        const float ux = r.dx, uy = r.dy, uz = r.dz;  // Vec3.normalized vec.zig:33-40: the search left r.d a unit vector
         const float udn = fmaf(ux, s.nx, fmaf(uy, s.ny, uz * s.nz));
         const float rx = fmaf(-2.0f * udn, s.nx, ux), ry = fmaf(-2.0f * udn, s.ny, uy), rz = fmaf(-2.0f * udn, s.nz, uz);  // reflect material.zig:112-114
         r.dx = rx; r.dy = ry; r.dz = rz;

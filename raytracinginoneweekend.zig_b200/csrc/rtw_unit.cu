@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(128) k_unit_shade(const DevScene sc, const Dev
     }
     Counters<false> cn;
     Hit h{0.0f, kMiss};
-    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, active, s_flat, sc.flat, sc, 0.001f, cn);
-    else if (active) h = closest_hit_bvh<false>(r, sc, 0.001f, cn);
+    float rl = 1.0f;  // 1/|d|: the searches normalise r in place and return distances
+    if (VARIANT == VAR_FLAT) h = closest_hit_flat<false>(r, active, s_flat, sc.flat, sc, 0.001f, cn, &rl);
+    else if (active) h = closest_hit_bvh<false>(r, sc, 0.001f, cn, &rl);
     if (!active) return;
     float *o = out + 20 * (size_t)k;
     for (int q = 0; q < 20; ++q) o[q] = 0.0f;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(128) k_unit_shade(const DevScene sc, const Dev
     else if (m.kind == 1u && m.param > 0.0f) { const float k = cbrtf(dw.uc); vec = make_float3(k * dw.x, k * dw.y, k * dw.z); }
     float3 beta = make_float3(1.f, 1.f, 1.f), L = make_float3(0.f, 0.f, 0.f);
     const bool go = shade<false>(sc, rp, r, prim, id, h.t, pixel, sample, bounce, beta, L, cn);
-    o[0] = h.t;
+    o[0] = h.t * rl;  // the reference's parameter
     o[1] = r.ox; o[2] = r.oy; o[3] = r.oz; o[4] = r.dx; o[5] = r.dy; o[6] = r.dz; o[7] = r.time;
     o[8] = beta.x; o[9] = beta.y; o[10] = beta.z;
     o[11] = L.x; o[12] = L.y; o[13] = L.z;

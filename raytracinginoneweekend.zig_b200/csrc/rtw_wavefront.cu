@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_flat(WfState st, const D
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // grid covers exactly the slot count
     const float4 o = st.ro[slot], d = st.rd[slot];
     const bool active = __float_as_uint(st.beta[slot].w) != kDead;
-    const Ray r{o.x, o.y, o.z, d.x, d.y, d.z, o.w};
+    Ray r{o.x, o.y, o.z, d.x, d.y, d.z, o.w};
     const Hit h = closest_hit_flat<STATS>(r, active, s_flat, sc.flat, sc, 0.001f, cn);
     if (active) {
-        st.rd[slot].w = h.t;
+        st.rd[slot] = make_float4(r.dx, r.dy, r.dz, h.t);  // the unit direction the search left, and the distance along it
         st.hit[slot] = h.slot;  // flat: prim id
     }
     if (STATS) cn.flush(rp.stats);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_bvh(WfState st, const De
                 if (__float_as_uint(st.beta[slot].w) != kDead) {
                     const float4 o = st.ro[slot], d = st.rd[slot];
                     r = Ray{o.x, o.y, o.z, d.x, d.y, d.z, o.w};
-                    if (tv.init(r, sc)) { st.rd[slot].w = tv.h.t; st.hit[slot] = kMiss; }
+                    if (tv.init(r, sc, 0.001f)) { st.rd[slot] = make_float4(r.dx, r.dy, r.dz, tv.h.t); st.hit[slot] = kMiss; }
                     else trav = true;
                 }
             }
@@ -165,12 +165,12 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_bvh(WfState st, const De
         const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
         const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
         if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
-            if (trav && tv.at_leaf()) done = tv.template leaf_step<STATS>(r, sc, 0.001f, stack, cn);
+            if (trav && tv.at_leaf()) done = tv.template leaf_step<STATS>(r, sc, stack, cn);
         }
-        if (trav && !done && !tv.at_leaf()) done = tv.template interior_step<STATS>(r, sc, 0.001f, stack, cn);
+        if (trav && !done && !tv.at_leaf()) done = tv.template interior_step<STATS>(r, sc, stack, cn);
         if (done) {
             trav = false;
-            st.rd[slot].w = tv.h.t;
+            st.rd[slot] = make_float4(r.dx, r.dy, r.dz, tv.h.t);  // unit direction + distance
             st.hit[slot] = tv.h.slot;  // BVH: leaf-order slot
         }
     }
