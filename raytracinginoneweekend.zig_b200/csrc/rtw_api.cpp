@@ -97,7 +97,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
                                     "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE",
-                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS"};
+                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE"};
 struct Options {
     std::map<std::string, std::string> v;
     const char *get(const char *name) const {
@@ -171,6 +171,7 @@ struct rtw_ctx {
     std::vector<std::pair<uint32_t, std::array<double, 10>>> host_inst_orig;  // ... their object-space fields
     std::vector<rtw_xform> host_xforms;
     uint32_t n_prims = 0;
+    uint32_t flat_feat = FF_ALL;  // FF_* features of the uploaded scene (selects the specialised flat megakernel)
     bool root_is_leaf = false;
 
     // wavefront variant: path-state slots
@@ -1103,6 +1104,16 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             }
         }
         fl.flags = sgroups.size() + mgroups.size() < 3 ? kFlatNoBounds : 0u;
+        uint32_t feat = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtw_prim &p = s->prims[i];
+            const bool sphere = p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE;
+            feat |= sphere ? FF_SPHERES : FF_RECTS;
+            if (sphere && p.xform >= 0) feat |= FF_TEX;  // instanced sphere: uv in object space (finalise_hit)
+        }
+        for (uint32_t i = 0; i < s->n_textures; ++i)
+            if (s->textures[i].kind != RTW_TEX_SOLID && s->textures[i].kind != RTW_TEX_CHECKER) feat |= FF_TEX;
+        ctx->flat_feat = feat;
         fl.n_sph_groups = (uint32_t)sgroups.size(); fl.n_big = (uint32_t)big_ids.size();
         fl.n_mov_groups = (uint32_t)mgroups.size(); fl.n_rect = (uint32_t)rect_ids.size();
         fl.off_sph = 0;
@@ -1258,7 +1269,15 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     // 1 first schedule, 2 second schedule at 9 CTAs/SM (56 registers, spills), 3 (default) second schedule at 8 CTAs/SM
     // (64 registers, no spills): measured 42.8 / 40.6 / 39.9 ms on scene 1 (1080p x 200 spp), 28.8 / 27.2 / 26.2 ms on C3
     const long fk = ctx->opt.num("RTW_FLAT_KERNEL", 3);
-    const int pooled = ((p->flags & RTW_FLAG_DETERMINISTIC) || env_set) ? 0 : (fk == 1 ? 1 : fk == 2 ? 2 : 3);
+    int pooled = ((p->flags & RTW_FLAG_DETERMINISTIC) || env_set) ? 0 : (fk == 1 ? 1 : fk == 2 ? 2 : 3);
+    // the default flat kernel exists in three specialisations on the scene's features (code for absent primitive and
+    // texture kinds compiled out); RTW_FLAT_SPECIALISE=0 runs the generic one.  Event-counter builds are generic.
+    if (pooled == 3 && variant == VAR_FLAT && !stats && ctx->opt.num("RTW_FLAT_SPECIALISE", 1) != 0) {
+        const uint32_t f = ctx->flat_feat;
+        if ((f & ~(uint32_t)FF_SPHERES) == 0) pooled = 4;
+        else if ((f & ~(uint32_t)(FF_SPHERES | FF_TEX)) == 0) pooled = 5;
+        else if ((f & ~(uint32_t)FF_RECTS) == 0) pooled = 6;
+    }
     const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
     if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (flat image %u B)", ctx->scene.flat.total_f4 * 16u);
     const int grid = per_sm * ctx->n_sms;

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kBlock, 9) k_megakernel_pooled(const DevScene 
 // lanes per scan of ~800; here Philox and the sin/cos/sqrt of the sampling run once per iteration at 32 lanes.
 // Samples are identical to every other kernel's (same counters, same maps): only the schedule differs.
 // ---------------------------------------------------------------------------------------------
-template <bool STATS, int MINB>
+template <bool STATS, int MINB, uint32_t FEAT>
 __global__ void __launch_bounds__(kBlock, MINB) k_megakernel_flat(const DevScene sc, const DevCamera cam, const DevRender rp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_flat = reinterpret_cast<float4 *>(smem_raw);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_megakernel_flat(const DevScene
             scatter_finish(r, pd, dw);
         }
         // ---- scan ----
-        const Hit h = closest_hit_flat<STATS>(r, alive, s_flat, sc.flat, sc, 0.001f, cn);
+        const Hit h = closest_hit_flat<STATS, FEAT>(r, alive, s_flat, sc.flat, sc, 0.001f, cn);
         // ---- A: what the hit decides without randomness ----
         if (alive) {
             cn.add(ST_RAYS);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_megakernel_flat(const DevScene
                 const DevPrim prim = sc.prims_flat[h.slot];
                 ++bounce;
                 // depth exhausted: the next rayColor call returns black before intersecting (main.zig:105-108)
-                alive = shade_prepare<STATS>(sc, r, prim, h.slot, h.t, beta, L, pd, cn) && bounce < rp.max_depth;
+                alive = shade_prepare<STATS, FEAT>(sc, r, prim, h.slot, h.t, beta, L, pd, cn) && bounce < rp.max_depth;
             }
             if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
         }
@@ -547,12 +547,16 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // host-side launchers (called from rtw_api.cpp through rtw_kernels.h)
 // ---------------------------------------------------------------------------------------------
 // POOLED: 0 = deterministic lane-owns-pixel kernel, 1 = pooled (flat: first schedule), 2 = flat second schedule at 9 CTAs
-// per SM (56 registers, a few spills), 3 = the same at 8 CTAs per SM (64 registers)
+// per SM (56 registers, a few spills), 3 = the same at 8 CTAs per SM (64 registers), 4 / 5 / 6 = 3 specialised on the scene's
+// features (FF_SPHERES, FF_SPHERES | FF_TEX, FF_RECTS; event-counter builds always run the generic kernel)
 template <int VARIANT, bool STATS, int POOLED>
 static auto mega_kernel_ptr() {
     if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS>;
-    else if constexpr (POOLED == 3) return k_megakernel_flat<STATS, 8>;
-    else if constexpr (POOLED == 2) return k_megakernel_flat<STATS, 9>;
+    else if constexpr (POOLED == 4) return k_megakernel_flat<STATS, 8, FF_SPHERES>;            // spheres, solid / checker textures
+    else if constexpr (POOLED == 5) return k_megakernel_flat<STATS, 8, FF_SPHERES | FF_TEX>;   // spheres, every texture kind
+    else if constexpr (POOLED == 6) return k_megakernel_flat<STATS, 8, FF_RECTS>;              // rects and boxes only, solid / checker
+    else if constexpr (POOLED == 3) return k_megakernel_flat<STATS, 8, FF_ALL>;
+    else if constexpr (POOLED == 2) return k_megakernel_flat<STATS, 9, FF_ALL>;
     else if constexpr (POOLED) return k_megakernel_pooled<VARIANT, STATS>;
     else return k_megakernel<VARIANT, STATS>;
 }
@@ -580,6 +584,7 @@ cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScen
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
+    RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
 #undef RTW_CASE
     return cudaErrorInvalidValue;
@@ -599,6 +604,7 @@ int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
+    RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
 #undef RTW_CASE
     return 0;

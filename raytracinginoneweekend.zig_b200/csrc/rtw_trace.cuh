@@ -313,7 +313,7 @@ __device__ __forceinline__ void rect_run(float ok, float dk, float oa, float da,
 
 // `r` comes in with any direction and leaves with the unit direction (normalise_ray); the returned Hit::t is the distance
 // along it.  `rl_out` (optional) receives 1/|d| for callers that report the reference's parameter t = s / |d|.
-template <bool STATS>
+template <bool STATS, uint32_t FEAT = FF_ALL>
 __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float4 *s, const FlatLayout &L,
                                                 const DevScene &sc, float t_min, Counters<STATS> &cn, float *rl_out = nullptr) {
     float rl;
@@ -326,7 +326,7 @@ __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float
     const uint32_t *ids = reinterpret_cast<const uint32_t *>(s + L.off_ids);
 
     // ---- big static spheres: c term about the reference point ----
-    {
+    if constexpr ((FEAT & FF_SPHERES) != 0u) {
         const float4 *sp = s + L.off_big;
         for (uint32_t i = 0; i < L.n_big; ++i) {
             const float4 a0 = sp[i];
@@ -346,7 +346,7 @@ __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float
     //      groups' members are tested, by every lane.  Against a vote and a branch per group this is 8 fewer instructions
     //      per bound; the reach (distance of the closest hit so far) is refreshed between chunks.  Scenes with fewer than
     //      three groups skip the bounds (L.flags & kFlatNoBounds): the test costs what it saves there ----
-    {
+    if constexpr ((FEAT & FF_SPHERES) != 0u) {
         const uint32_t ng = L.n_sph_groups + L.n_mov_groups;
         const float4 *bnd = s + L.off_bounds;  // padded to a multiple of four with NaN radii (never pass)
         const float4 *sph = s + L.off_sph, *mov = s + L.off_mov;
@@ -391,7 +391,7 @@ __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float
     }
     // ---- boxes: up to six rects that are the faces of one axis-aligned box of an instance's object space (the reference's
     //      Box, hittable.zig:429-470, and rooms): one transform, three slabs, six parameter comparisons ----
-    {
+    if constexpr ((FEAT & FF_RECTS) != 0u) {
         const float4 *bx = s + L.off_boxes;
         for (uint32_t q = 0; q < L.n_boxes; ++q, bx += kBoxF4) {
             const float4 A = bx[0], B = bx[1];
@@ -443,7 +443,7 @@ __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float
     }
     // ---- rects: runs of equal (instance transform, orientation); consecutive runs of one instance (a box = three
     //      runs) share the object-space ray, which is therefore set up once per instance, not once per run ----
-    {
+    if constexpr ((FEAT & FF_RECTS) != 0u) {
         const uint4 *runs = reinterpret_cast<const uint4 *>(s + L.off_runs);
         float o[3] = {u.ox, u.oy, u.oz}, d[3] = {u.dx, u.dy, u.dz};
         for (uint32_t q = 0; q < L.n_runs; ++q) {
@@ -601,13 +601,13 @@ struct Surface {
     bool is_sphere;       // plain sphere: uv = getSphereUv(outward normal), computed lazily by the image texture
 };
 
-template <bool STATS>
+template <bool STATS, uint32_t FEAT = FF_ALL>
 __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, float t, const DevScene &sc,
                                                 Counters<STATS> &cn) {
     Surface s;
     const uint32_t kind = __float_as_uint(p.b.w) & 0xFFu;
     s.px = fmaf(t, r.dx, r.ox); s.py = fmaf(t, r.dy, r.oy); s.pz = fmaf(t, r.dz, r.oz);  // Ray.at ray.zig:10-12
-    if (kind == PK_SPHERE) {
+    if (!(FEAT & FF_RECTS) || ((FEAT & FF_SPHERES) && kind == PK_SPHERE)) {
         cn.add(ST_SPHERE_FINAL);
         const float cx = fmaf(p.b.x, r.time, p.a.x), cy = fmaf(p.b.y, r.time, p.a.y), cz = fmaf(p.b.z, r.time, p.a.z);
         const float inv_r = rcp_approx(p.a.w);
@@ -615,7 +615,7 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
         s.is_sphere = true;
         s.u = 0.0f; s.v = 0.0f; s.ru = 1.0f; s.rv = 1.0f;
         const uint32_t xf = __float_as_uint(p.b.w) >> 20;
-        if (xf) {  // instanced sphere: getSphereUv sees the OBJECT-space normal (hittable.zig:127 inside Translate/RotateY)
+        if ((FEAT & FF_TEX) && xf) {  // instanced sphere: getSphereUv sees the OBJECT-space normal (hittable.zig:127 inside Translate/RotateY)
             const DevXform x = sc.xforms[xf - 1];
             const float ux = fmaf(x.c, s.onx, -x.s * s.onz), uz = fmaf(x.s, s.onx, x.c * s.onz);
             const float pi = 3.14159265358979323846f;
@@ -690,7 +690,7 @@ __device__ __forceinline__ float perlin_turb(const DevPerlin &pn, float x, float
     return fabsf(accum);
 }
 
-template <bool STATS>
+template <bool STATS, uint32_t FEAT = FF_ALL>
 __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, const Surface &s, Counters<STATS> &cn) {
     DevTexture tx = sc.textures[ti];
     // Checker (texture.zig:79-82): sign(sin(10x) sin(10y) sin(10z)) < 0 -> odd.  sin(10 x) < 0 iff
@@ -703,7 +703,7 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, cons
         const int par = (int)floorf(s.px * k) + (int)floorf(s.py * k) + (int)floorf(s.pz * k);
         tx = sc.textures[(par & 1) ? tx.a : tx.b];
     }
-    if (tx.kind <= 1u) return make_float3(tx.r, tx.g, tx.bl);  // solid texture.zig:46-55 (a checker still here = nesting beyond the guard: refused at upload)
+    if (!(FEAT & FF_TEX) || tx.kind <= 1u) return make_float3(tx.r, tx.g, tx.bl);  // solid texture.zig:46-55 (a checker still here = nesting beyond the guard: refused at upload)
     if (tx.kind == 2u) {  // noise texture.zig:100-104
         cn.add(ST_TEX_NOISE);
         const float v = 0.5f * (1.0f + sinf(tx.scale * s.pz + 10.0f * perlin_turb(sc.perlins[tx.a], s.px, s.py, s.pz)));
@@ -805,21 +805,21 @@ struct Pending {
     uint32_t kind;     // RTW_MAT_* of the surface being left
 };
 
-template <bool STATS>
+template <bool STATS, uint32_t FEAT = FF_ALL>
 __device__ __forceinline__ bool shade_prepare(const DevScene &sc, Ray &r, const DevPrim &prim, uint32_t prim_id, float t,
                                               float3 &beta, float3 &L, Pending &pd, Counters<STATS> &cn) {
-    const Surface s = finalise_hit<STATS>(r, prim, t, sc, cn);
+    const Surface s = finalise_hit<STATS, FEAT>(r, prim, t, sc, cn);
     const DevMaterial m = sc.materials[sc.prim_material[prim_id]];
     pd.kind = m.kind;
     if (m.kind == 3u) {  // diffuse_light: emitted on both faces, never scatters (material.zig:97-109)
         cn.add(ST_EMIT);
-        const float3 e = texture_value<STATS>(sc, m.tex, s, cn);
+        const float3 e = texture_value<STATS, FEAT>(sc, m.tex, s, cn);
         L.x = fmaf(beta.x, e.x, L.x); L.y = fmaf(beta.y, e.y, L.y); L.z = fmaf(beta.z, e.z, L.z);
         return false;
     }
     if (m.kind == 0u) {  // diffuse material.zig:44-52: direction = normal + unit vector
         cn.add(ST_SC_DIFFUSE);
-        const float3 a = texture_value<STATS>(sc, m.tex, s, cn);
+        const float3 a = texture_value<STATS, FEAT>(sc, m.tex, s, cn);
         beta.x *= a.x; beta.y *= a.y; beta.z *= a.z;
         r.dx = s.nx; r.dy = s.ny; r.dz = s.nz;
     } else {
@@ -876,7 +876,7 @@ __device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, R
                                       uint32_t prim_id, float t, uint32_t pixel, uint32_t sample, uint32_t bounce,
                                       float3 &beta, float3 &L, Counters<STATS> &cn) {
     Pending pd;
-    if (!shade_prepare<STATS>(sc, r, prim, prim_id, t, beta, L, pd, cn)) return false;
+    if (!shade_prepare<STATS, FF_ALL>(sc, r, prim, prim_id, t, beta, L, pd, cn)) return false;
     const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.philox_keys);
     scatter_finish(r, pd, make_draw(rn, false));
     return true;
