@@ -412,7 +412,8 @@ def main():
                     "steps": e2e_steps, "call": "rtw_cuda_upload_scene + rtw_cuda_render (host buffers)" if world == 1
                     else "upload + accumulate + NCCL reduce + resolve + D2H image"},
             "gpu_launches": 2 * args.steps,
-            "kernel": {"name": "k_megakernel", "variant": st["variant_used"], "ms_per_launch": kernel_ms,
+            "kernel": {"name": "k_megakernel_flat<STATS=0, MINB=8, FEAT=FF_SPHERES>" if st["variant_used"] == 1 else "k_megakernel_bvh<0>",
+                       "variant": st["variant_used"], "ms_per_launch": kernel_ms,
                        "flops_per_ray_counted": counted_flops(st) / max(1, st["rays"])},
             "strong": strong,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

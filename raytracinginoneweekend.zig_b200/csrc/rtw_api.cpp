@@ -97,7 +97,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
                                     "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE",
-                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE"};
+                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES"};
 struct Options {
     std::map<std::string, std::string> v;
     const char *get(const char *name) const {
@@ -659,6 +659,32 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     wprims.resize(n);
     std::vector<Box3d> &boxes = ctx->scratch_boxes;
     boxes.resize(n);
+    // Spheres tested individually ahead of the groups ("big"): |r| >= kBigSphereRadius always (their c term needs the
+    // reference-point form), and in scenes small enough for the flat scan also the few static spheres that dwarf the rest
+    // (> 2.5 x the median radius, at most eight: the three r = 1 spheres of main.zig:202-218 among r = 0.2 ones) — inside a
+    // group they inflate its bound (a vote passes a group roughly in proportion to R^2), alone they cost one
+    // discriminant each and, being hit early, shorten the reach for every bound after them.
+    double big_thr = kBigSphereRadius;
+    if (n <= kFlatAutoMax && ctx->opt.num("RTW_MID_SPHERES", 1) != 0) {
+        std::vector<double> radii;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtw_prim &p = s->prims[i];
+            if (p.kind == RTW_PRIM_SPHERE) radii.push_back(std::fabs(p.v[3]));
+            else if (p.kind == RTW_PRIM_MOVING_SPHERE) radii.push_back(std::fabs(p.v[8]));
+        }
+        if (radii.size() >= 8) {
+            std::vector<double> sorted(radii);
+            std::nth_element(sorted.begin(), sorted.begin() + sorted.size() / 2, sorted.end());
+            const double cut = 2.5 * sorted[sorted.size() / 2];
+            uint32_t n_mid = 0;
+            double smallest = kBigSphereRadius;
+            for (uint32_t i = 0; i < n; ++i) {
+                const rtw_prim &p = s->prims[i];
+                if (p.kind == RTW_PRIM_SPHERE && p.xform < 0 && std::fabs(p.v[3]) > cut) { ++n_mid; smallest = std::min(smallest, std::fabs(p.v[3])); }
+            }
+            if (n_mid > 0 && n_mid <= 8) big_thr = smallest;
+        }
+    }
     // reference point for big spheres: centroid of the centres of everything that is not big (summed per fixed
     // chunk, chunks in order: the same bits on every machine)
     std::vector<std::array<double, 4>> cen_part(n_chunks_of(n), std::array<double, 4>{0, 0, 0, 0});
@@ -682,7 +708,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             } else {
                 boxes[i] = leaf_box(s, s->prims[i]);
             }
-            if (p.kind == RTW_PRIM_SPHERE && std::fabs(p.v[3]) >= kBigSphereRadius) continue;
+            if (p.kind == RTW_PRIM_SPHERE && p.xform < 0 && std::fabs(p.v[3]) >= big_thr) continue;
             for (int a = 0; a < 3; ++a) acc[a] += 0.5 * (boxes[i].mn[a] + boxes[i].mx[a]);
             acc[3] += 1.0;
         }
@@ -723,7 +749,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             d.a = make_float4((float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]);
             d.b = make_float4(0.f, 0.f, 0.f, 0.f);
             meta = PK_SPHERE;
-            if (std::fabs(p.v[3]) >= kBigSphereRadius && bigs.size() < 0xFFEu) {
+            if ((std::fabs(p.v[3]) >= kBigSphereRadius || (p.xform < 0 && std::fabs(p.v[3]) >= big_thr)) && bigs.size() < 0xFFEu) {
                 // q = point of the sphere surface nearest the scene's centre of interest
                 double dir[3] = {cen[0] - p.v[0], cen[1] - p.v[1], cen[2] - p.v[2]};
                 double len = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
@@ -771,7 +797,7 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     for_chunks(n, bt, [&](uint32_t chunk, uint32_t lo, uint32_t hi) {
         for (uint32_t i = lo; i < hi; ++i) {
             const rtw_prim &p = wprims[i];
-            if (p.xform >= 0 || (p.kind == RTW_PRIM_SPHERE && std::fabs(p.v[3]) >= kBigSphereRadius)) special[chunk].push_back(i);
+            if (p.xform >= 0 || (p.kind == RTW_PRIM_SPHERE && std::fabs(p.v[3]) >= big_thr)) special[chunk].push_back(i);
             else lower(i);
         }
     });
@@ -965,8 +991,14 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             }
             for (auto &g : groups) std::sort(g.begin(), g.end());
         };
-        auto sgroups = make_groups(stat_ids), mgroups = make_groups(mov_ids);
-        refine_groups(sgroups);
+        // Static and moving spheres are grouped TOGETHER, by position alone (a static sphere is a moving one with zero
+        // velocity: DevPrim::b.xyz = 0, and fma(0, time, c) = c exactly, so the BVH leaves' test stays bit-identical):
+        // tighter bounds than per-kind groups over the same cells, one member code path in the scan, fewer padding slots.
+        std::vector<uint32_t> small_ids(stat_ids);
+        small_ids.insert(small_ids.end(), mov_ids.begin(), mov_ids.end());
+        std::sort(small_ids.begin(), small_ids.end());
+        std::vector<std::vector<uint32_t>> sgroups;  // (no separate static groups any more; the layout keeps the slot)
+        auto mgroups = make_groups(small_ids);
         refine_groups(mgroups);
         std::vector<float4> sph, big, mov, rect, bounds;
         std::vector<uint32_t> ids;

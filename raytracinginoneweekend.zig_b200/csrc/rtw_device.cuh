@@ -81,13 +81,14 @@ struct DevPerlin {
 };
 
 // Shared-memory image of a small scene for the flat scan, as one blob of float4 (offsets in float4
-// units).  Primitives are SEGMENTED BY KIND and small spheres are packed into spatial GROUPS of four
-// behind a bounding sphere, so that a whole warp can skip a group with one vote:
-//   bounds     : 1 x float4 per group, static groups then moving groups: (cx, cy, cz, R), the smallest ball enclosing the
-//                members over the shutter interval; padded to a multiple of four with NaN radii (never pass)
-//   sph groups : 4 x float4  = 4 members (cx, cy, cz, r^2)
-//   big        : 1 x float4  (cx, cy, cz, r^2) per big static sphere; DevBigSphere i in scene.bigs
-//   mov groups : 8 x float4  = 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}
+// units).  Primitives are SEGMENTED BY KIND and small spheres — static and moving together, by position — are packed into
+// spatial GROUPS of four behind a bounding sphere, so that a whole warp can skip a group:
+//   big        : 1 x float4  (cx, cy, cz, r^2) per individually tested static sphere (|r| >= 64, or one of the few that dwarf
+//                the rest of a small scene); DevBigSphere i in scene.bigs
+//   groups     : 8 x float4  = 4 members x {(cbx, cby, cbz, r^2), (vx, vy, vz, r)}: centre(time) = cb + vel * time, vel = 0
+//                for a static sphere (FlatLayout::n_mov_groups / off_mov; the n_sph_groups / off_sph slots are unused: 0)
+//   bounds     : 1 x float4 per group: (cx, cy, cz, R), the smallest ball enclosing the members over the shutter interval;
+//                padded to a multiple of four with NaN radii (never pass): the scan tests four bounds per warp reduction
 //   rect       : 2 x float4 per rect: (a0, a1, b0, b1), (k, bits(prim id), -, -), sorted into RUNS of equal
 //                (instance transform, orientation) so the object-space ray is set up once per run and the
 //                inner loop is specialised per orientation and branch-free
@@ -95,11 +96,11 @@ struct DevPerlin {
 //                transform, PK_XY/XZ/YZ, first rect, count); the runs of one transform are adjacent
 //   boxes      : kBoxF4 x float4 per box: rects of one instance that are faces of ONE axis-aligned box of its object space —
 //                the reference's `Box` (6 faces, hittable.zig:429-470) and rooms like the Cornell box's five walls (faces
-//                missing is fine).  (x0, x1, y0, y1), (z0, z1, bits(xform slot + 1 or 0), bits(face mask)), four prim ids,
-//                (two prim ids, cos, sin), (tx, ty, tz, -): ids in Box.init order z1, z0, y1, y0, x1, x0
-//                (hittable.zig:437-442), the instance's composed transform inline.  Tested as three slabs, see box_face in
-//                rtw_trace.cuh; rects that belong to a box are not in the runs.
-//   ids        : uint32 prim id per member slot, in the order sph | big | mov
+//                missing is fine: id -1).  (x0, x1, y0, y1), (z0, z1, bits(xform slot + 1 or 0), bits(face mask)), four prim
+//                ids, (two prim ids, cos, sin), (tx, ty, tz, -): ids in Box.init order z1, z0, y1, y0, x1, x0
+//                (hittable.zig:437-442), the instance's composed transform inline.  Tested as three slabs (entry and exit
+//                face), see closest_hit_flat in rtw_trace.cuh; rects that belong to a box are not in the runs.
+//   ids        : uint32 prim id per slot, in the order big (padded to x4) | four per group
 // Unused member slots have r^2 = -1 (never hit).
 constexpr uint32_t kRunSameXform = 0x80000000u;
 constexpr uint32_t kBoxF4 = 5;

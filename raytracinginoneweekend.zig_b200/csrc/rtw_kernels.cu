@@ -508,11 +508,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(const DevScene sc, uint32_t n,
     normal[3 * idx] = s.nx; normal[3 * idx + 1] = s.ny; normal[3 * idx + 2] = s.nz;
     if (uv) {
         float u = __fdividef(s.u, s.ru), v = __fdividef(s.v, s.rv);  // rect: numerator / denominator (lazy division)
-        if (s.is_sphere) {
-            const float pi = 3.14159265358979323846f;
-            u = (atan2f(-s.onz, s.onx) + pi) / (2.0f * pi);
-            v = acosf(fminf(fmaxf(-s.ony, -1.0f), 1.0f)) / pi;
-        }
+        if (s.is_sphere) sphere_uv(s.onx, s.ony, s.onz, u, v);
         uv[2 * idx] = u; uv[2 * idx + 1] = v;
     }
 }

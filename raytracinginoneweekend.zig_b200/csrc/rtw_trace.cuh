@@ -337,20 +337,20 @@ __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float
                 cn.add(ST_SPHERE_ROOTS);
                 const float c = big_sphere_c(u, sc.bigs[i]);
                 float t;
-                if (sphere_root(c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[4 * L.n_sph_groups + i]);
+                if (sphere_root(c, bp, d0, t_min, best.t, t)) flat_consider(best, t, ids[i]);
             }
         }
     }
-    // ---- sphere groups, static then moving, FOUR AT A TIME: the four bounds as straight-line code, each lane collecting
+    // ---- sphere groups (static and moving spheres together, grouped by position), FOUR AT A TIME: the four bounds as straight-line code, each lane collecting
     //      its own pass bits; ONE warp reduction (REDUX.OR) turns them into the set of groups somebody needs; then only those
     //      groups' members are tested, by every lane.  Against a vote and a branch per group this is 8 fewer instructions
     //      per bound; the reach (distance of the closest hit so far) is refreshed between chunks.  Scenes with fewer than
     //      three groups skip the bounds (L.flags & kFlatNoBounds): the test costs what it saves there ----
     if constexpr ((FEAT & FF_SPHERES) != 0u) {
-        const uint32_t ng = L.n_sph_groups + L.n_mov_groups;
+        const uint32_t ng = L.n_mov_groups;
         const float4 *bnd = s + L.off_bounds;  // padded to a multiple of four with NaN radii (never pass)
-        const float4 *sph = s + L.off_sph, *mov = s + L.off_mov;
-        const uint32_t mov_ids = 4 * L.n_sph_groups + ((L.n_big + 3u) & ~3u);
+        const float4 *mov = s + L.off_mov;
+        const uint32_t mov_ids = (L.n_big + 3u) & ~3u;  // ids: big (padded to x4) | four per group
 #pragma unroll 1
         for (uint32_t base = 0; base < ng; base += 4u, bnd += 4) {
             const uint32_t nb = min(4u, ng - base);
@@ -368,24 +368,21 @@ __device__ __forceinline__ Hit closest_hit_flat(Ray &r, bool active, const float
                 const uint32_t g = base + (uint32_t)__ffs((int)m) - 1u;
                 m &= m - 1u;
                 if (active) cn.add(ST_SPHERE_TESTS, 4);
-                if (g < L.n_sph_groups) {
-                    const float4 *gp = sph + 4 * g;
-                    const uint4 id = *reinterpret_cast<const uint4 *>(ids + 4 * g);
-                    flat_static_pair<STATS>(u, gp[0], gp[1], id.x, id.y, active, t_min, best, cn);
-                    flat_static_pair<STATS>(u, gp[2], gp[3], id.z, id.w, active, t_min, best, cn);
-                } else {  // centre(time) = cb + vel*time (hittable.zig:219-221)
-                    const uint32_t gm = g - L.n_sph_groups;
-                    const float4 *gp = mov + 8 * gm;
-                    const uint4 id = *reinterpret_cast<const uint4 *>(ids + mov_ids + 4 * gm);
-                    if (active) cn.add(ST_MOVING_TESTS, 4);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float4 a0 = gp[4 * h], v0 = gp[1 + 4 * h], a1 = gp[2 + 4 * h], v1 = gp[3 + 4 * h];
-                        const float4 c0 = make_float4(fmaf(v0.x, u.time, a0.x), fmaf(v0.y, u.time, a0.y), fmaf(v0.z, u.time, a0.z), a0.w);
-                        const float4 c1 = make_float4(fmaf(v1.x, u.time, a1.x), fmaf(v1.y, u.time, a1.y), fmaf(v1.z, u.time, a1.z), a1.w);
-                        flat_static_pair<STATS>(u, c0, c1, h ? id.z : id.x, h ? id.w : id.y, active, t_min, best, cn);
-                    }
+                // every member is a (centre, velocity) pair: centre(time) = cb + vel*time (hittable.zig:219-221), vel = 0 for
+                // a static sphere (static and moving spheres share the groups: they are formed by position alone)
+                const float4 *gp = mov + 8 * g;
+                const uint4 id = *reinterpret_cast<const uint4 *>(ids + mov_ids + 4 * g);
+                const float4 a0 = gp[0], v0 = gp[1], a1 = gp[2], v1 = gp[3], a2 = gp[4], v2 = gp[5], a3 = gp[6], v3 = gp[7];
+                if (STATS) {
+                    if (active) cn.add(ST_MOVING_TESTS, (v0.x != 0.f || v0.y != 0.f || v0.z != 0.f) + (v1.x != 0.f || v1.y != 0.f || v1.z != 0.f) +
+                                                            (v2.x != 0.f || v2.y != 0.f || v2.z != 0.f) + (v3.x != 0.f || v3.y != 0.f || v3.z != 0.f));
                 }
+                const float4 c0 = make_float4(fmaf(v0.x, u.time, a0.x), fmaf(v0.y, u.time, a0.y), fmaf(v0.z, u.time, a0.z), a0.w);
+                const float4 c1 = make_float4(fmaf(v1.x, u.time, a1.x), fmaf(v1.y, u.time, a1.y), fmaf(v1.z, u.time, a1.z), a1.w);
+                const float4 c2 = make_float4(fmaf(v2.x, u.time, a2.x), fmaf(v2.y, u.time, a2.y), fmaf(v2.z, u.time, a2.z), a2.w);
+                const float4 c3 = make_float4(fmaf(v3.x, u.time, a3.x), fmaf(v3.y, u.time, a3.y), fmaf(v3.z, u.time, a3.z), a3.w);
+                flat_static_pair<STATS>(u, c0, c1, id.x, id.y, active, t_min, best, cn);
+                flat_static_pair<STATS>(u, c2, c3, id.z, id.w, active, t_min, best, cn);
             }
         }
     }
@@ -591,6 +588,38 @@ __device__ __forceinline__ Hit closest_hit_bvh(Ray &r, const DevScene &sc, float
 // Hit record of the winning primitive (computed once per ray, not per candidate as the reference
 // does at hittable.zig:118-128).
 // ---------------------------------------------------------------------------------------------
+// getSphereUv (hittable.zig:145-150) needs atan2 and acos of the outward normal: CUDA's atan2f + acosf were 9 % of all
+// warp instructions of the image-texture config at 9.4 lanes (profiles/r02_c).  Polynomials fitted on [0, 1] (least squares on
+// Chebyshev nodes, errors measured over 2*10^6 fp32 arguments): |atan error| <= 1.8e-7 rad, |acos error| <= 3.5e-7 rad, i.e.
+// u, v to 6e-8 / 1.2e-7 — 2.4e-4 of a texel of the 2048-wide asset.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? mn * rcp_approx(mx) : 0.0f;  // atan2(0, 0) = 0 like libm
+    const float z = a * a;
+    float p = -0.0048311310820281506f;
+    p = fmaf(p, z, 0.024756666272878647f); p = fmaf(p, z, -0.060218989849090576f); p = fmaf(p, z, 0.09967915713787079f);
+    p = fmaf(p, z, -0.14040136337280273f); p = fmaf(p, z, 0.1997368186712265f); p = fmaf(p, z, -0.33332303166389465f);
+    p = fmaf(p, z, 0.9999999403953552f);
+    float r = p * a;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.0f ? 3.14159265358979323846f - r : r;
+    return copysignf(r, y);
+}
+__device__ __forceinline__ float fast_acos(float x) {  // x in [-1, 1]
+    const float ax = fabsf(x);
+    float p = 0.0022513726726174355f;
+    p = fmaf(p, ax, -0.011012407019734383f); p = fmaf(p, ax, 0.026749366894364357f); p = fmaf(p, ax, -0.048724427819252014f);
+    p = fmaf(p, ax, 0.08873733878135681f); p = fmaf(p, ax, -0.21458369493484497f); p = fmaf(p, ax, 1.5707961320877075f);
+    const float r = sqrt_approx(1.0f - ax) * p;
+    return x < 0.0f ? 3.14159265358979323846f - r : r;
+}
+// u, v of getSphereUv for the outward unit normal n (hittable.zig:145-150)
+__device__ __forceinline__ void sphere_uv(float nx, float ny, float nz, float &u, float &v) {
+    u = (fast_atan2(-nz, nx) + 3.14159265358979323846f) * 0.15915494309189533577f;
+    v = fast_acos(fminf(fmaxf(-ny, -1.0f), 1.0f)) * 0.31830988618379067154f;
+}
+
 struct Surface {
     float px, py, pz;     // hit point, world space
     float nx, ny, nz;     // face-corrected normal (HitRecord.normal)
@@ -618,9 +647,7 @@ __device__ __forceinline__ Surface finalise_hit(const Ray &r, const DevPrim &p, 
         if ((FEAT & FF_TEX) && xf) {  // instanced sphere: getSphereUv sees the OBJECT-space normal (hittable.zig:127 inside Translate/RotateY)
             const DevXform x = sc.xforms[xf - 1];
             const float ux = fmaf(x.c, s.onx, -x.s * s.onz), uz = fmaf(x.s, s.onx, x.c * s.onz);
-            const float pi = 3.14159265358979323846f;
-            s.u = (atan2f(-uz, ux) + pi) / (2.0f * pi);
-            s.v = acosf(fminf(fmaxf(-s.ony, -1.0f), 1.0f)) / pi;
+            sphere_uv(ux, s.ony, uz, s.u, s.v);
             s.is_sphere = false;  // uv already final
         }
     } else {
@@ -712,11 +739,7 @@ __device__ __forceinline__ float3 texture_value(const DevScene &sc, int ti, cons
     // image texture.zig:121-144 — nearest texel by truncation, alpha==0 -> (0,0,1)
     cn.add(ST_TEX_IMAGE);
     float u = __fdividef(s.u, s.ru), v = __fdividef(s.v, s.rv);
-    if (s.is_sphere) {  // getSphereUv hittable.zig:145-150
-        const float pi = 3.14159265358979323846f;
-        u = (atan2f(-s.onz, s.onx) + pi) / (2.0f * pi);
-        v = acosf(fminf(fmaxf(-s.ony, -1.0f), 1.0f)) / pi;
-    }
+    if (s.is_sphere) sphere_uv(s.onx, s.ony, s.onz, u, v);  // getSphereUv hittable.zig:145-150
     const DevImage im = sc.images[tx.a];
     const float uc = fminf(fmaxf(u, 0.0f), 1.0f);
     const float vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
