@@ -10,6 +10,8 @@ sys.path.insert(0, ROOT)
 import torch
 import rtw_b200
 from rtw_b200 import abi
+if os.environ.get("RTW_AB_LIB"):  # A/B of two builds inside one GPU call: point the loader at a saved copy of librtw_cuda.so
+    rtw_b200.build.CUDA_LIB = os.path.abspath(os.environ["RTW_AB_LIB"])
 
 ctx = rtw_b200.Context(0)
 scenes = {}
