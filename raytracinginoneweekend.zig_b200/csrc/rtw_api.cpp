@@ -31,7 +31,7 @@ namespace {
 // Spheres at least this large get the reference-point form of |o-c|^2 - r^2 (rtw_trace.cuh).
 constexpr double kBigSphereRadius = 64.0;
 // Scenes up to this many primitives default to the warp-uniform flat scan (measured crossover).
-constexpr uint32_t kFlatAutoMax = 128;  // measured crossover on sphere scenes: flat 20 % ahead at 66 prims, level at 145, BVH 10 % ahead at 198
+constexpr uint32_t kFlatAutoMax = 256;  // measured crossover on sphere scenes (round 2 kernels, 1080p x 50 spp): flat 27 % ahead at 145 prims, 12 % at 198, level at 256, BVH 10 % ahead at 326
 constexpr uint32_t kLbvhAutoMin = 1u << 16;  // scenes at least this large build their BVH on the device
 constexpr uint32_t kFlatHardMax = 6000;  // the shared-memory image must stay under ~200 KB
 constexpr uint32_t kMaxCheckerDepth = 8;  // = the guard of the device loop in texture_value (rtw_trace.cuh)
@@ -836,6 +836,19 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     ctx->stats.ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_bvh).count();
     ctx->stats.bvh_builder = bvh_on_device ? RTW_BVH_BUILDER_LBVH : RTW_BVH_BUILDER_SAH;
 
+    // which primitive / texture kinds the scene has: selects the specialised megakernels (FF_* in rtw_device.cuh)
+    {
+        uint32_t feat = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtw_prim &p = s->prims[i];
+            const bool sphere = p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE;
+            feat |= sphere ? FF_SPHERES : FF_RECTS;
+            if (sphere && p.xform >= 0) feat |= FF_TEX;  // instanced sphere: uv in object space (finalise_hit)
+        }
+        for (uint32_t i = 0; i < s->n_textures; ++i)
+            if (s->textures[i].kind != RTW_TEX_SOLID && s->textures[i].kind != RTW_TEX_CHECKER) feat |= FF_TEX;
+        ctx->flat_feat = feat;
+    }
     // ---- shared-memory image for the flat scan: segmented by kind, small spheres in groups of four --------
     FlatLayout fl{};
     std::vector<float4> blob;
@@ -1136,16 +1149,6 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             }
         }
         fl.flags = sgroups.size() + mgroups.size() < 3 ? kFlatNoBounds : 0u;
-        uint32_t feat = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const rtw_prim &p = s->prims[i];
-            const bool sphere = p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE;
-            feat |= sphere ? FF_SPHERES : FF_RECTS;
-            if (sphere && p.xform >= 0) feat |= FF_TEX;  // instanced sphere: uv in object space (finalise_hit)
-        }
-        for (uint32_t i = 0; i < s->n_textures; ++i)
-            if (s->textures[i].kind != RTW_TEX_SOLID && s->textures[i].kind != RTW_TEX_CHECKER) feat |= FF_TEX;
-        ctx->flat_feat = feat;
         fl.n_sph_groups = (uint32_t)sgroups.size(); fl.n_big = (uint32_t)big_ids.size();
         fl.n_mov_groups = (uint32_t)mgroups.size(); fl.n_rect = (uint32_t)rect_ids.size();
         fl.off_sph = 0;
@@ -1304,7 +1307,7 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
     int pooled = ((p->flags & RTW_FLAG_DETERMINISTIC) || env_set) ? 0 : (fk == 1 ? 1 : fk == 2 ? 2 : 3);
     // the default flat kernel exists in three specialisations on the scene's features (code for absent primitive and
     // texture kinds compiled out); RTW_FLAT_SPECIALISE=0 runs the generic one.  Event-counter builds are generic.
-    if (pooled == 3 && variant == VAR_FLAT && !stats && ctx->opt.num("RTW_FLAT_SPECIALISE", 1) != 0) {
+    if (pooled == 3 && !stats && ctx->opt.num("RTW_FLAT_SPECIALISE", 1) != 0) {  // (the BVH megakernel has the spheres-only specialisation)
         const uint32_t f = ctx->flat_feat;
         if ((f & ~(uint32_t)FF_SPHERES) == 0) pooled = 4;
         else if ((f & ~(uint32_t)(FF_SPHERES | FF_TEX)) == 0) pooled = 5;

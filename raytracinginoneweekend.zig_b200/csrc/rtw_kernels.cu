@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_megakernel_flat(const DevScene
 // new traversals start — all in one "service" phase that therefore runs reasonably full.
 // ---------------------------------------------------------------------------------------------
 
-template <bool STATS>
+template <bool STATS, uint32_t FEAT>
 __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, const DevCamera cam, const DevRender rp) {
     Counters<STATS> cn;
     const uint32_t lane = threadIdx.x & 31;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
                     const DevPrim prim = sc.prims_bvh[tv.h.slot];
                     const uint32_t prim_id = sc.bvh_prim_id[tv.h.slot];
                     ++bounce;
-                    alive = shade<STATS>(sc, rp, r, prim, prim_id, tv.h.t, pixel, cur_sample, bounce, beta, L, cn) &&
+                    alive = shade<STATS, FEAT>(sc, rp, r, prim, prim_id, tv.h.t, pixel, cur_sample, bounce, beta, L, cn) &&
                             bounce < rp.max_depth;  // main.zig:105-108
                 }
                 if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
             const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
             const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
             if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
-                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS>(r, sc, stack, cn);
+                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS, FEAT>(r, sc, stack, cn);
             }
         }
         // ---- interior phase ----
@@ -547,8 +547,9 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // features (FF_SPHERES, FF_SPHERES | FF_TEX, FF_RECTS; event-counter builds always run the generic kernel)
 template <int VARIANT, bool STATS, int POOLED>
 static auto mega_kernel_ptr() {
-    if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS>;
-    else if constexpr (POOLED == 4) return k_megakernel_flat<STATS, 8, FF_SPHERES>;            // spheres, solid / checker textures
+    if constexpr (POOLED == 4 && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_SPHERES>;  // spheres, solid / checker textures
+    else if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_ALL>;
+    else if constexpr (POOLED == 4) return k_megakernel_flat<STATS, 9, FF_SPHERES>;            // spheres, solid / checker textures
     else if constexpr (POOLED == 5) return k_megakernel_flat<STATS, 8, FF_SPHERES | FF_TEX>;   // spheres, every texture kind
     else if constexpr (POOLED == 6) return k_megakernel_flat<STATS, 8, FF_RECTS>;              // rects and boxes only, solid / checker
     else if constexpr (POOLED == 3) return k_megakernel_flat<STATS, 8, FF_ALL>;
@@ -576,12 +577,13 @@ static size_t mega_smem(int variant, const DevScene &sc) {
 cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled >= 1) pooled = 1;
+    if (variant == VAR_BVH && pooled >= 1) pooled = (pooled == 4 && !stats) ? 4 : 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
     RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
+    RTW_CASE(VAR_BVH, false, 4);
 #undef RTW_CASE
     return cudaErrorInvalidValue;
 }
@@ -596,12 +598,13 @@ static int occ_t(size_t smem) {
 
 int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled >= 1) pooled = 1;
+    if (variant == VAR_BVH && pooled >= 1) pooled = (pooled == 4 && !stats) ? 4 : 1;
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
     RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
+    RTW_CASE(VAR_BVH, false, 4);
 #undef RTW_CASE
     return 0;
 }

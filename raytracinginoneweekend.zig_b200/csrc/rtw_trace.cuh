@@ -195,11 +195,11 @@ __device__ __forceinline__ bool rect_test(const Ray &r, const DevPrim &p, uint32
     return h;
 }
 
-template <bool STATS>
+template <bool STATS, uint32_t FEAT = FF_ALL>
 __device__ __forceinline__ bool prim_test(const Ray &u, const DevPrim &p, const DevScene &sc, float s_min, float s_max,
                                           float &s_out, Counters<STATS> &cn) {
     const uint32_t kind = __float_as_uint(p.b.w) & 0xFFu;
-    if (kind == PK_SPHERE) return sphere_test<STATS>(u, p, sc.bigs, s_min, s_max, s_out, cn);
+    if (!(FEAT & FF_RECTS) || ((FEAT & FF_SPHERES) && kind == PK_SPHERE)) return sphere_test<STATS>(u, p, sc.bigs, s_min, s_max, s_out, cn);
     return rect_test<STATS>(u, p, kind, sc.xforms, s_min, s_max, s_out, cn);
 }
 
@@ -546,7 +546,7 @@ struct BvhTraversal {
     }
 
     // one leaf visit (precondition: at_leaf()): the only primitive-test site.  Returns true when finished.
-    template <bool STATS>
+    template <bool STATS, uint32_t FEAT = FF_ALL>
     __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
                                               Counters<STATS> &cn) {
         const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
@@ -555,7 +555,7 @@ struct BvhTraversal {
             DevPrim p;
             ldg256(sc.prims_bvh + slot, p.a, p.b);
             float t;
-            if (prim_test<STATS>(r, p, sc, s_min, h.t, t, cn)) {
+            if (prim_test<STATS, FEAT>(r, p, sc, s_min, h.t, t, cn)) {
                 const uint32_t id = __ldg(sc.bvh_prim_id + slot);
                 if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
             }
@@ -894,12 +894,12 @@ __device__ __forceinline__ void scatter_finish(Ray &r, const Pending &pd, const 
 
 // prepare + draw + finish in one call (deterministic, BVH and wavefront kernels, unit probe).  Returns true when the
 // path continues with `r` replaced by the scattered ray.
-template <bool STATS>
+template <bool STATS, uint32_t FEAT = FF_ALL>
 __device__ __forceinline__ bool shade(const DevScene &sc, const DevRender &rp, Ray &r, const DevPrim &prim,
                                       uint32_t prim_id, float t, uint32_t pixel, uint32_t sample, uint32_t bounce,
                                       float3 &beta, float3 &L, Counters<STATS> &cn) {
     Pending pd;
-    if (!shade_prepare<STATS, FF_ALL>(sc, r, prim, prim_id, t, beta, L, pd, cn)) return false;
+    if (!shade_prepare<STATS, FEAT>(sc, r, prim, prim_id, t, beta, L, pd, cn)) return false;
     const uint4 rn = philox4x32_10(make_uint4(pixel, sample, bounce, 0u), rp.philox_keys);
     scatter_finish(r, pd, make_draw(rn, false));
     return true;
