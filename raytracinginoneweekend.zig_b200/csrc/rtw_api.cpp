@@ -97,7 +97,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
                                     "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE",
-                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES"};
+                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES", "RTW_GROUP_ROUND"};
 struct Options {
     std::map<std::string, std::string> v;
     const char *get(const char *name) const {
@@ -865,17 +865,23 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
         }
         // spatial groups of exactly 4 (the last one may be short): recursive median splits on the widest
         // axis of the centroids, the left half always a multiple of four so no slot is wasted
+        // Groups of at most four by recursive median splits on the widest axis of the centroids.  The scan tests bounds
+        // four at a time, so the NUMBER of groups is rounded up to a multiple of four (option RTW_GROUP_ROUND=0: exactly
+        // ceil(n / 4) groups of four): the bounds that would be padding enclose three spheres instead of nothing.
+        const bool round_groups = ctx->opt.num("RTW_GROUP_ROUND", 1) != 0;
         auto make_groups = [&](const std::vector<uint32_t> &sub) {
             std::vector<std::vector<uint32_t>> groups;
             std::vector<uint32_t> work(sub);
-            struct Range { size_t lo, hi; };
+            struct Range { size_t lo, hi, g; };  // [lo, hi) becomes g groups
             std::vector<Range> st;
-            if (!work.empty()) st.push_back({0, work.size()});
+            size_t G = (work.size() + 3) / 4;
+            if (round_groups && G >= 3) G = std::min((G + 3) / 4 * 4, work.size());
+            if (!work.empty()) st.push_back({0, work.size(), G});
             while (!st.empty()) {
                 const Range rg = st.back();
                 st.pop_back();
                 const size_t cnt = rg.hi - rg.lo;
-                if (cnt <= 4) {
+                if (rg.g <= 1) {
                     std::vector<uint32_t> m(work.begin() + rg.lo, work.begin() + rg.hi);
                     std::sort(m.begin(), m.end());
                     groups.push_back(m);
@@ -887,11 +893,18 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
                     for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], cen(work[k], a)); mx[a] = std::max(mx[a], cen(work[k], a)); }
                 int ax = 0;
                 for (int a = 1; a < 3; ++a) if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
-                const size_t left = 4 * ((cnt / 4 + 1) / 2);  // multiple of 4, about half
+                // g_left of the g groups go left with a proportional share of the spheres, at most four per group on
+                // either side
+                const size_t gl = rg.g / 2, gr = rg.g - gl;
+                size_t left = (cnt * gl + rg.g / 2) / rg.g;
+                left = std::min(left, 4 * gl);
+                if (cnt - left > 4 * gr) left = cnt - 4 * gr;
+                left = std::max<size_t>(left, gl);                    // no empty group
+                if (cnt - left < gr) left = cnt - gr;
                 std::nth_element(work.begin() + rg.lo, work.begin() + rg.lo + left, work.begin() + rg.hi,
                                  [&](uint32_t x, uint32_t y) { return cen(x, ax) < cen(y, ax); });
-                st.push_back({rg.lo, rg.lo + left});
-                st.push_back({rg.lo + left, rg.hi});
+                st.push_back({rg.lo, rg.lo + left, gl});
+                st.push_back({rg.lo + left, rg.hi, gr});
             }
             return groups;
         };
