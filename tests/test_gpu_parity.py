@@ -553,6 +553,46 @@ def test_flat_and_bvh_render_the_same_paths(rtw, ctx, knobs):
     assert not np.array_equal(a, c)  # a different seed gives different samples
 
 
+def test_flat_layout_heuristics_change_the_work_not_the_result(rtw, oracle, ctx):
+    """The flat scan's layout heuristics — the few spheres that dwarf the rest tested individually (RTW_MID_SPHERES), the
+    number of groups rounded up to a multiple of four (RTW_GROUP_ROUND), the kernel specialised on the scene's features
+    (RTW_FLAT_SPECIALISE) — decide WHICH tests run, never what a test returns: same closest hits (ids equal; t to the last
+    bits: an individually tested sphere takes its c term about a reference point), same paths."""
+    rng = np.random.default_rng(77)
+    for sid, grid in ((1, 3), (1, 5)):
+        hs = rtw.HostScene(sid, grid=grid)
+        osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
+        rays = scene_util.random_rays(rng, 40000, extent=6.0)
+        rays[:20000, 0:3] = np.array([13.0, 2.0, 3.0]) + rng.normal(size=(20000, 3)) * 0.05
+        oid = osc.trace_rays(rays, 64)[0]
+        base = None
+        counts = []
+        for opts in ({}, {"RTW_MID_SPHERES": "0"}, {"RTW_GROUP_ROUND": "0"}, {"RTW_MID_SPHERES": "0", "RTW_GROUP_ROUND": "0"}):
+            with ctx.options(**opts):
+                ctx.upload_scene(hs.desc, keep=hs)
+                gid, gt = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_FLAT)[:2]
+                cam = hs.camera()
+                ctx.render(cam, ctx.params(96, 64, 0, 8, 8, 50, 1, rtw.abi.FLAG_COUNT_EVENTS, 5, hs.background))
+                counts.append(ctx.stats()["sphere_tests"])
+            assert (gid != oid).mean() <= 1e-3
+            if base is None:
+                base = (gid, gt)
+            else:
+                assert np.array_equal(gid, base[0])
+                hit = gid != MISS
+                assert np.abs(gt[hit] - base[1][hit]).max() <= 2e-6 * max(1.0, float(np.abs(base[1][hit]).max()))
+        assert len(set(counts)) > 1  # the switches did change the work
+    # specialised vs generic kernel: identical paths, only the order of the fp32 sums per pixel may differ
+    hs = rtw.HostScene(1)
+    ctx.upload_scene(hs.desc, keep=hs)
+    cam = hs.camera()
+    p = ctx.params(120, 80, 0, 32, 32, 50, 1, 0, 11, hs.background)
+    a = ctx.render(cam, p, want_accum=True)[1]
+    with ctx.options(RTW_FLAT_SPECIALISE="0"):
+        b = ctx.render(cam, p, want_accum=True)[1]
+    assert np.allclose(a, b, rtol=1e-4, atol=1e-3)
+
+
 def test_spp_split_equals_full_render(rtw, ctx, knobs):
     """The multi-GPU partition: sample ranges rendered separately and summed == the full range
     (Philox is keyed by the absolute sample index).  Only fp32 summation order differs."""
