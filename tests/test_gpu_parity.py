@@ -553,6 +553,43 @@ def test_flat_and_bvh_render_the_same_paths(rtw, ctx, knobs):
     assert not np.array_equal(a, c)  # a different seed gives different samples
 
 
+@pytest.mark.parametrize("n_static,n_moving,big", [(1, 0, 0), (0, 1, 0), (2, 3, 0), (5, 4, 1), (9, 0, 2), (0, 13, 0), (17, 20, 3),
+                                                   (8, 8, 8), (33, 31, 1), (60, 60, 0), (100, 100, 2)])
+def test_flat_groups_any_count_and_mix(rtw, oracle, ctx, n_static, n_moving, big):
+    """Sphere scenes of every size and mix of kinds (static / moving / a few that dwarf the rest / a huge ground): group
+    sizes of two to four, a last chunk with padding, no-bounds mode (< 3 groups), unified static + moving groups.  Flat
+    scan == BVH bit for bit (ids and distances), reference-order probe == oracle bit for bit, production ids == f64 oracle
+    almost everywhere."""
+    rng = np.random.default_rng(1000 * n_static + 10 * n_moving + big)
+    b = scene_util.DescBuilder()
+    mats = [b.diffuse(b.solid((0.5, 0.5, 0.5))), b.metal((0.7, 0.6, 0.5), 0.1), b.glass(1.5)]
+    b.sphere((0.0, -1000.0, 0.0), 1000.0, mats[0])
+    for _ in range(n_static):
+        c = rng.uniform(-5, 5, 3); c[1] = rng.uniform(0.1, 1.0)
+        b.sphere(tuple(c), float(rng.uniform(0.1, 0.3)), mats[int(rng.integers(0, 3))])
+    for _ in range(n_moving):
+        c = rng.uniform(-5, 5, 3); c[1] = rng.uniform(0.1, 1.0)
+        c1 = c + np.array([0.0, rng.uniform(0, 0.5), 0.0])
+        b.moving_sphere(tuple(c), tuple(c1), 0.0, 1.0, float(rng.uniform(0.1, 0.3)), mats[int(rng.integers(0, 3))])
+    for _ in range(big):
+        c = rng.uniform(-4, 4, 3); c[1] = 1.0
+        b.sphere(tuple(c), float(rng.uniform(0.9, 1.3)) * (-1.0 if rng.uniform() < 0.2 else 1.0), mats[int(rng.integers(0, 3))])
+    desc = b.build()
+    osc = oracle.OracleScene.from_desc(desc, keep=desc)
+    ctx.upload_scene(desc, keep=desc)
+    rays = scene_util.random_rays(rng, 20000, extent=6.0)
+    rays[:8000, 0:3] = np.array([13.0, 2.0, 3.0]) + rng.normal(size=(8000, 3)) * 0.05
+    o32 = osc.trace_rays(rays, 32)
+    assert (o32[0] != MISS).mean() > 0.2
+    for variant in (rtw.abi.VARIANT_MEGA_FLAT, rtw.abi.VARIANT_MEGA_BVH):
+        g = ctx.trace_rays(rays, 32, variant)
+        assert np.array_equal(g[0], o32[0]) and np.array_equal(g[1], o32[1])
+    a = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_FLAT)
+    c = ctx.trace_rays(rays, 0, rtw.abi.VARIANT_MEGA_BVH)
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+    assert (a[0] != osc.trace_rays(rays, 64)[0]).mean() <= 1e-3
+
+
 def test_flat_layout_heuristics_change_the_work_not_the_result(rtw, oracle, ctx):
     """The flat scan's layout heuristics — the few spheres that dwarf the rest tested individually (RTW_MID_SPHERES), the
     number of groups rounded up to a multiple of four (RTW_GROUP_ROUND), the kernel specialised on the scene's features
