@@ -1,9 +1,12 @@
 // rtw_kernels.cu — production kernels (fp32, FMA contraction on), sm_100a.
 //
-//   k_megakernel_pooled<FLAT,STATS>  K1 for scenes of <= 64 primitives: flat scan out of shared memory
-//   k_megakernel_bvh<STATS>          K1 for larger scenes: BVH traversal as a per-lane state machine
+//   k_megakernel_flat<STATS,MINB,FEAT> K1 for scenes of <= 256 primitives (default): flat scan out of shared memory, second
+//                                    schedule (one Philox block + one evaluation of the sampling maps per iteration for the
+//                                    whole warp), specialised on the scene's features (FF_* in rtw_device.cuh)
+//   k_megakernel_bvh<STATS,FEAT>     K1 for larger scenes: BVH traversal as a per-lane state machine
+//   k_megakernel_pooled<VARIANT,STATS> first flat schedule (RTW_FLAT_KERNEL=1, kept for A/B measurements)
 //   k_megakernel<VARIANT,STATS>      K1, deterministic form (lane owns a pixel; RTW_FLAG_DETERMINISTIC)
-//        all three replace the loop nest src/main.zig:382-394 and everything below it
+//        all four replace the loop nest src/main.zig:382-394 and everything below it
 //   k_resolve / k_resolve4           K4: replaces src/main.zig:395-400 (average, sqrt, clamp, x256 -> u8, row flip),
 //                                    optionally summing several (peer-mapped) accumulation buffers first
 //   k_probe<VARIANT>                 production-arithmetic closest-hit probe (parity instrument)

@@ -206,10 +206,11 @@ __device__ __forceinline__ bool prim_test(const Ray &u, const DevPrim &p, const 
 // ---------------------------------------------------------------------------------------------
 // Flat scan: the scene staged in shared memory as a FlatLayout blob.  Every lane reads the same
 // record (smem broadcast), so the scan itself has no divergence; loop bodies are branch-free up to
-// the (rare) accept path and unrolled for ILP.  Small spheres sit in spatial groups of four behind
-// a bounding sphere: each lane tests the bound, ONE warp vote decides whether anybody needs the
-// group, and if nobody does the whole warp skips its four members — culling without divergence.
-// ALL 32 lanes must call this (inactive lanes pass active = false): it contains warp votes.
+// the (rare) accept path and unrolled for ILP.  Small spheres (static and moving together) sit in spatial
+// groups of up to four behind a bounding sphere: each lane tests four bounds, ONE warp reduction (REDUX.OR)
+// decides which of the four groups anybody needs, and the whole warp tests only those groups' members —
+// culling without divergence.  The ground and the few spheres that dwarf the rest are tested first, individually.
+// ALL 32 lanes must call this (inactive lanes pass active = false): it contains warp reductions.
 // Grouping changes the visiting order, so the reference's tie rule ("later list element wins",
 // hittable.zig:235-242) is applied explicitly: a candidate replaces the current hit if t < best, or
 // t == best and its prim id is larger.
