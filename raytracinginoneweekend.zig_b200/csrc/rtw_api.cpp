@@ -97,7 +97,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
                                     "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE",
-                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES", "RTW_GROUP_ROUND"};
+                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES", "RTW_GROUP_ROUND", "RTW_BVH_KERNEL"};
 struct Options {
     std::map<std::string, std::string> v;
     const char *get(const char *name) const {
@@ -1326,6 +1326,8 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
         else if ((f & ~(uint32_t)(FF_SPHERES | FF_TEX)) == 0) pooled = 5;
         else if ((f & ~(uint32_t)FF_RECTS) == 0) pooled = 6;
     }
+    // option RTW_BVH_KERNEL: 1 = per-lane state machine, 2 = per-warp ray queue in shared memory (k_megakernel_bvhq)
+    if (variant == VAR_BVH && pooled >= 1 && ctx->opt.num("RTW_BVH_KERNEL", 1) == 2) pooled = pooled == 4 ? 8 : 7;
     const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
     if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (flat image %u B)", ctx->scene.flat.total_f4 * 16u);
     const int grid = per_sm * ctx->n_sms;

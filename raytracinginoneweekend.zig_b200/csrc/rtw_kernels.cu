@@ -4,9 +4,11 @@
 //                                    schedule (one Philox block + one evaluation of the sampling maps per iteration for the
 //                                    whole warp), specialised on the scene's features (FF_* in rtw_device.cuh)
 //   k_megakernel_bvh<STATS,FEAT>     K1 for larger scenes: BVH traversal as a per-lane state machine
+//   k_megakernel_bvhq<STATS,FEAT,SLOTS,MINB> the same paths with a per-warp ray queue in shared memory (RTW_BVH_KERNEL=2; measured
+//                                    slower than the state machine, profiles/r02_l: kept for A/B measurements)
 //   k_megakernel_pooled<VARIANT,STATS> first flat schedule (RTW_FLAT_KERNEL=1, kept for A/B measurements)
 //   k_megakernel<VARIANT,STATS>      K1, deterministic form (lane owns a pixel; RTW_FLAG_DETERMINISTIC)
-//        all four replace the loop nest src/main.zig:382-394 and everything below it
+//        all of these replace the loop nest src/main.zig:382-394 and everything below it
 //   k_resolve / k_resolve4           K4: replaces src/main.zig:395-400 (average, sqrt, clamp, x256 -> u8, row flip),
 //                                    optionally summing several (peer-mapped) accumulation buffers first
 //   k_probe<VARIANT>                 production-arithmetic closest-hit probe (parity instrument)
@@ -399,6 +401,184 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// BVH megakernel, second schedule: a per-WARP ray queue in shared memory.  ncu on the state machine above
+// (profiles/r02_j, r02_k): the interior phase runs at 18.5-18.9 of 32 lanes — a lane whose traversal is finished sits idle
+// until >= 24 lanes have gathered for the service phase.  Here a warp owns SLOTS (> 32) path slots in shared memory
+// (ray, hit, path state: 18 words each, field-major so that lanes touching different slots hit different banks) and
+// two rings of slot numbers:
+//     ready   rays waiting to be traversed          done   finished traversals waiting to be shaded
+// A lane whose traversal ends pushes its slot on `done` and takes the next slot from `ready` AT ONCE (ballot + popc
+// ranks), so every lane is traversing as long as `ready` is not empty; when `done` holds 32 slots the service phase
+// shades them at 32 of 32 lanes (whichever lanes produced them), replaces dead paths from the pool and pushes the new rays
+// on `ready`.  With 64 slots and 32 lanes traversing, ready + done = 32: `ready` runs empty exactly when `done` is full.
+// Only the traversal state lives in registers; the path state (beta, L, pixel, sample, bounce) never does outside the
+// service phase.  Same samples, same paths as every other kernel (Philox counters): only the schedule differs.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { QF_OX, QF_OY, QF_OZ, QF_DX, QF_DY, QF_DZ, QF_TIME, QF_T, QF_HIT, QF_PIXEL, QF_SAMPLE, QF_BOUNCE,
+                  QF_BR, QF_BG, QF_BB, QF_LR, QF_LG, QF_LB, QF_COUNT };
+constexpr uint32_t kQEmpty = 0xFFFFFFFFu;  // QF_PIXEL of a slot without a path
+
+constexpr int kBvhqSlots = 64;
+
+template <bool STATS, uint32_t FEAT, int SLOTS, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_megakernel_bvhq(const DevScene sc, const DevCamera cam, const DevRender rp) {
+    static_assert(SLOTS > 32 && SLOTS <= 255, "slot numbers are bytes; 32 lanes traverse while the rest wait in the rings");
+    __shared__ uint32_t q_words[kBlock / 32][QF_COUNT * SLOTS];
+    __shared__ uint8_t q_rings[kBlock / 32][2][SLOTS];
+    uint32_t *const S = q_words[threadIdx.x >> 5];
+    uint8_t *const ready_q = q_rings[threadIdx.x >> 5][0], *const done_q = q_rings[threadIdx.x >> 5][1];
+#define QW(f, s) S[(f) * SLOTS + (s)]
+#define QF(f, s) __uint_as_float(S[(f) * SLOTS + (s)])
+    auto wrap = [](uint32_t x) { return x >= (uint32_t)SLOTS ? x - (uint32_t)SLOTS : x; };
+
+    Counters<STATS> cn;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t pool_next = 0, pool_end = 0, pool_tx = 0, pool_ty = 0, pool_s0 = 0;
+    bool more = true;
+    // every slot starts on `done` without a path: the first service phases start the first paths
+    for (uint32_t s = lane; s < (uint32_t)SLOTS; s += 32u) { QW(QF_PIXEL, s) = kQEmpty; done_q[s] = (uint8_t)s; }
+    uint32_t ready_head = 0, ready_count = 0, done_head = 0, done_count = SLOTS, live = SLOTS;
+    __syncwarp();
+
+    Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+    BvhTraversal tv;
+    uint32_t stack[kBvhStack];
+    tv.sp = 0; tv.cur = 0;
+    uint32_t my = 0;   // slot of the ray this lane is traversing
+    bool trav = false, fin = false;  // fin: traversal finished, slot not yet pushed on `done`
+    for (;;) {
+        // ---- service phase: shade up to 32 finished traversals, one per lane ----
+        const uint32_t thr = min(rp.service_threshold, live > 32u ? live - 32u : 1u);
+        if (done_count >= thr) {
+            const uint32_t n = min(32u, done_count);
+            const bool mine = lane < n;
+            const uint32_t s = mine ? done_q[wrap(done_head + lane)] : 0u;
+            done_head = wrap(done_head + n); done_count -= n;
+            Ray q{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+            float3 beta = make_float3(1.0f, 1.0f, 1.0f), L = make_float3(0.0f, 0.0f, 0.0f);
+            uint32_t pixel = mine ? QW(QF_PIXEL, s) : kQEmpty, cur_sample = 0, bounce = 0;
+            bool alive = mine && pixel != kQEmpty;
+            if (alive) {
+                cn.add(ST_RAYS);
+                q = Ray{QF(QF_OX, s), QF(QF_OY, s), QF(QF_OZ, s), QF(QF_DX, s), QF(QF_DY, s), QF(QF_DZ, s), QF(QF_TIME, s)};
+                beta = make_float3(QF(QF_BR, s), QF(QF_BG, s), QF(QF_BB, s));
+                L = make_float3(QF(QF_LR, s), QF(QF_LG, s), QF(QF_LB, s));
+                cur_sample = QW(QF_SAMPLE, s); bounce = QW(QF_BOUNCE, s);
+                const uint32_t hit = QW(QF_HIT, s);
+                if (hit == kMiss) {  // main.zig:109-112
+                    L.x = fmaf(beta.x, rp.bg_r, L.x); L.y = fmaf(beta.y, rp.bg_g, L.y); L.z = fmaf(beta.z, rp.bg_b, L.z);
+                    alive = false;
+                } else {
+                    const DevPrim prim = sc.prims_bvh[hit];
+                    const uint32_t prim_id = sc.bvh_prim_id[hit];
+                    ++bounce;
+                    alive = shade<STATS, FEAT>(sc, rp, q, prim, prim_id, QF(QF_T, s), pixel, cur_sample, bounce, beta, L, cn) &&
+                            bounce < rp.max_depth;  // main.zig:105-108
+                }
+                if (!alive) red_add_v4(rp.accum + pixel, L.x, L.y, L.z, 1.0f);
+            }
+            // ---- hand new paths to the slots without one ----
+            for (;;) {
+                const uint32_t need = __ballot_sync(0xffffffffu, mine && !alive);
+                if (!need) break;
+                if (pool_next == pool_end) {
+                    if (!more) break;
+                    uint32_t b = 0;
+                    if (lane == 0) b = atomicAdd(rp.tile_counter, 1u);
+                    b = __shfl_sync(0xffffffffu, b, 0);
+                    if (b >= rp.n_batches) { more = false; break; }
+                    const uint32_t sb = b / rp.n_tiles, tile = b - sb * rp.n_tiles;
+                    pool_ty = tile / rp.tiles_x; pool_tx = tile - pool_ty * rp.tiles_x;
+                    pool_s0 = rp.spp_begin + sb * rp.batch_spp;
+                    pool_next = 0;
+                    pool_end = 32u * min(rp.batch_spp, rp.spp_end - pool_s0);
+                }
+                const uint32_t take = min((uint32_t)__popc(need), pool_end - pool_next);
+                const uint32_t rank = __popc(need & lt_mask);
+                if (mine && !alive && rank < take) {
+                    const uint32_t idx = pool_next + rank;
+                    const uint32_t pl = idx & 31u;
+                    const uint32_t i = pool_tx * 8 + (pl & 7), j = pool_ty * 4 + (pl >> 3);
+                    if (i < rp.width && j < rp.height) {  // ragged edge tiles: the index is consumed, no path starts
+                        pixel = j * rp.width + i;
+                        cur_sample = pool_s0 + (idx >> 5);
+                        q = camera_ray(cam, rp, pixel, i, j, cur_sample);
+                        beta = make_float3(1.0f, 1.0f, 1.0f);
+                        L = make_float3(0.0f, 0.0f, 0.0f);
+                        bounce = 0;
+                        alive = true;
+                        cn.add(ST_PATHS);
+                    }
+                }
+                pool_next += take;
+            }
+            // ---- write the slots back; rays go on `ready`, slots that found no new path are retired ----
+            const uint32_t m_go = __ballot_sync(0xffffffffu, alive);
+            if (alive) {
+                QW(QF_OX, s) = __float_as_uint(q.ox); QW(QF_OY, s) = __float_as_uint(q.oy); QW(QF_OZ, s) = __float_as_uint(q.oz);
+                QW(QF_DX, s) = __float_as_uint(q.dx); QW(QF_DY, s) = __float_as_uint(q.dy); QW(QF_DZ, s) = __float_as_uint(q.dz);
+                QW(QF_TIME, s) = __float_as_uint(q.time);
+                QW(QF_PIXEL, s) = pixel; QW(QF_SAMPLE, s) = cur_sample; QW(QF_BOUNCE, s) = bounce;
+                QW(QF_BR, s) = __float_as_uint(beta.x); QW(QF_BG, s) = __float_as_uint(beta.y); QW(QF_BB, s) = __float_as_uint(beta.z);
+                QW(QF_LR, s) = __float_as_uint(L.x); QW(QF_LG, s) = __float_as_uint(L.y); QW(QF_LB, s) = __float_as_uint(L.z);
+                ready_q[wrap(wrap(ready_head + ready_count) + (uint32_t)__popc(m_go & lt_mask))] = (uint8_t)s;
+            }
+            ready_count += (uint32_t)__popc(m_go);
+            live -= n - (uint32_t)__popc(m_go);
+            __syncwarp();
+        }
+        if (live == 0u) break;  // pool exhausted and every path finished
+        // ---- fetch: lanes without a traversal take the next rays of `ready` ----
+        {
+            const uint32_t need = __ballot_sync(0xffffffffu, !trav);
+            const uint32_t take = min((uint32_t)__popc(need), ready_count);
+            if (take) {
+                const uint32_t rank = __popc(need & lt_mask);
+                if (!trav && rank < take) {
+                    my = ready_q[wrap(ready_head + rank)];
+                    r = Ray{QF(QF_OX, my), QF(QF_OY, my), QF(QF_OZ, my), QF(QF_DX, my), QF(QF_DY, my), QF(QF_DZ, my), QF(QF_TIME, my)};
+                    fin = tv.init(r, sc, 0.001f);  // true: empty scene, the ray is a miss already
+                    trav = !fin;
+                    // shade continues from the unit direction (normalise_ray)
+                    QW(QF_DX, my) = __float_as_uint(r.dx); QW(QF_DY, my) = __float_as_uint(r.dy); QW(QF_DZ, my) = __float_as_uint(r.dz);
+                }
+                ready_head = wrap(ready_head + take); ready_count -= take;
+            }
+        }
+        // ---- leaf phase: lanes parked at a leaf wait until enough of them have gathered (or nobody is left descending) ----
+        {
+            const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
+            const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
+            if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
+                if (trav && tv.at_leaf()) { fin = tv.template leaf_step<STATS, FEAT>(r, sc, stack, cn); trav = !fin; }
+            }
+        }
+        // ---- interior phase ----
+#pragma unroll 1
+        for (uint32_t k = 0; k < rp.steps_per_round; ++k) {
+            if (trav && !tv.at_leaf()) { fin = tv.template interior_step<STATS>(r, sc, stack, cn); trav = !fin; }
+        }
+        // ---- finished traversals go on `done` ----
+        {
+            const uint32_t m_fin = __ballot_sync(0xffffffffu, fin);
+            if (m_fin) {
+                if (fin) {
+                    QW(QF_T, my) = __float_as_uint(tv.h.t); QW(QF_HIT, my) = tv.h.slot;
+                    done_q[wrap(wrap(done_head + done_count) + (uint32_t)__popc(m_fin & lt_mask))] = (uint8_t)my;
+                    fin = false;
+                }
+                done_count += (uint32_t)__popc(m_fin);
+                __syncwarp();
+            }
+        }
+    }
+#undef QW
+#undef QF
+    if (STATS) cn.flush(rp.stats);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4 resolve: out = 256 * clamp(sqrt(sum / spp), 0, 0.999) truncated to u8, written to row H-1-j.
 // Sums up to kMaxResolveBufs accumulation buffers first; with peer access enabled those may live on
 // other GPUs, i.e. the cross-GPU reduction and the resolve are one kernel over NVLink peer memory.
@@ -550,7 +730,9 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // features (FF_SPHERES, FF_SPHERES | FF_TEX, FF_RECTS; event-counter builds always run the generic kernel)
 template <int VARIANT, bool STATS, int POOLED>
 static auto mega_kernel_ptr() {
-    if constexpr (POOLED == 4 && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_SPHERES>;  // spheres, solid / checker textures
+    if constexpr (POOLED == 8 && VARIANT == VAR_BVH) return k_megakernel_bvhq<STATS, FF_SPHERES, kBvhqSlots, 8>;  // ray-queue schedule
+    else if constexpr (POOLED == 7 && VARIANT == VAR_BVH) return k_megakernel_bvhq<STATS, FF_ALL, kBvhqSlots, 7>;
+    else if constexpr (POOLED == 4 && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_SPHERES>;  // spheres, solid / checker textures
     else if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_ALL>;
     else if constexpr (POOLED == 4) return k_megakernel_flat<STATS, 9, FF_SPHERES>;            // spheres, solid / checker textures
     else if constexpr (POOLED == 5) return k_megakernel_flat<STATS, 8, FF_SPHERES | FF_TEX>;   // spheres, every texture kind
@@ -573,6 +755,13 @@ static cudaError_t launch_mega_t(const DevScene &sc, const DevCamera &cam, const
     return cudaGetLastError();
 }
 
+// BVH kernels: 1 = state machine, 4 = its spheres-only specialisation, 7 = ray-queue schedule, 8 = its spheres-only
+// specialisation; event-counter builds run the generic kernel of the schedule
+static int bvh_pooled(int pooled, bool stats) {
+    if (pooled == 7 || pooled == 8) return (pooled == 8 && !stats) ? 8 : 7;
+    return (pooled == 4 && !stats) ? 4 : 1;
+}
+
 static size_t mega_smem(int variant, const DevScene &sc) {
     return variant == VAR_FLAT ? (size_t)sc.flat.total_f4 * sizeof(float4) : 0;
 }
@@ -580,13 +769,13 @@ static size_t mega_smem(int variant, const DevScene &sc) {
 cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled >= 1) pooled = (pooled == 4 && !stats) ? 4 : 1;
+    if (variant == VAR_BVH && pooled >= 1) pooled = bvh_pooled(pooled, stats);
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return launch_mega_t<V, S, P>(sc, cam, rp, grid, smem, st)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
     RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
-    RTW_CASE(VAR_BVH, false, 4);
+    RTW_CASE(VAR_BVH, false, 4); RTW_CASE(VAR_BVH, false, 7); RTW_CASE(VAR_BVH, true, 7); RTW_CASE(VAR_BVH, false, 8);
 #undef RTW_CASE
     return cudaErrorInvalidValue;
 }
@@ -601,13 +790,13 @@ static int occ_t(size_t smem) {
 
 int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc) {
     const size_t smem = mega_smem(variant, sc);
-    if (variant == VAR_BVH && pooled >= 1) pooled = (pooled == 4 && !stats) ? 4 : 1;
+    if (variant == VAR_BVH && pooled >= 1) pooled = bvh_pooled(pooled, stats);
 #define RTW_CASE(V, S, P) if (variant == V && stats == S && pooled == P) return occ_t<V, S, P>(smem)
     RTW_CASE(VAR_FLAT, false, 0); RTW_CASE(VAR_FLAT, true, 0); RTW_CASE(VAR_FLAT, false, 1); RTW_CASE(VAR_FLAT, true, 1);
     RTW_CASE(VAR_FLAT, false, 2); RTW_CASE(VAR_FLAT, true, 2); RTW_CASE(VAR_FLAT, false, 3); RTW_CASE(VAR_FLAT, true, 3);
     RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
-    RTW_CASE(VAR_BVH, false, 4);
+    RTW_CASE(VAR_BVH, false, 4); RTW_CASE(VAR_BVH, false, 7); RTW_CASE(VAR_BVH, true, 7); RTW_CASE(VAR_BVH, false, 8);
 #undef RTW_CASE
     return 0;
 }

@@ -22,7 +22,8 @@ struct ResolveArgs {
 
 // rtw_kernels.cu (production arithmetic)
 // pooled: 0 = deterministic lane-owns-pixel kernel, 1 = pooled path queue (BVH state machine / flat first schedule),
-//         2 / 3 = flat second schedule (k_megakernel_flat) at 9 / 8 CTAs per SM; >= 1 all mean the state machine for the BVH variant
+//         2 / 3 = flat second schedule (k_megakernel_flat) at 9 / 8 CTAs per SM, 4 / 5 / 6 = 3 specialised on the scene's features;
+//         BVH variant: 7 / 8 = ray-queue schedule (generic / spheres only), 4 = spheres-only state machine, every other value >= 1 = state machine
 cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScene &sc, const DevCamera &cam,
                               const DevRender &rp, int grid, cudaStream_t st);
 int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &sc);

@@ -717,6 +717,34 @@ def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, knobs, sid
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+@pytest.mark.parametrize("sid,grid,W,H,spp", [(1, 11, 203, 117, 9), (1, 3, 64, 40, 33), (2, 11, 97, 61, 5), (6, 11, 120, 120, 12), (4, 11, 80, 60, 8)])
+def test_bvh_ray_queue_schedule_renders_the_same_paths(rtw, ctx, sid, grid, W, H, spp):
+    """k_megakernel_bvhq (RTW_BVH_KERNEL=2: per-warp ray queue in shared memory, traversing lanes refilled from the ring) is
+    another schedule of the same paths as the per-lane state machine: identical Philox keys and closest hits => identical
+    event counts and per-sample radiance; only the fp32 summation order per pixel differs.  Generic and spheres-only
+    builds, ragged frames, threshold extremes (service phase at 1 and at 32 finished rays)."""
+    hs = rtw.HostScene(sid, grid=grid)
+    ctx.upload_scene(hs.desc, keep=hs)
+    cam = hs.camera(aspect=W / H)
+    bvh = rtw.abi.VARIANT_MEGA_BVH
+    for flag in (rtw.abi.FLAG_COUNT_EVENTS, 0):
+        p = ctx.params(W, H, 0, spp, spp, 50, bvh, flag, 42, hs.background)
+        a = ctx.render(cam, p, want_accum=True)
+        st_a = ctx.stats()
+        for opts in ({}, {"RTW_BVH_THRESH": "1", "RTW_BVH_LEAF": "1"}, {"RTW_BVH_THRESH": "32", "RTW_BVH_STEPS": "7"}):
+            with ctx.options(RTW_BVH_KERNEL="2", **opts):
+                b = ctx.render(cam, p, want_accum=True)
+                st_b = ctx.stats()
+            assert (b[1][..., 3] == spp).all()
+            if flag:
+                assert st_b["paths"] == st_a["paths"] == W * H * spp and st_b["rays"] == st_a["rays"]
+                for k in ("scatter_diffuse", "scatter_metal", "scatter_dielectric", "emit_hits", "sphere_finalise", "node_tests"):
+                    assert st_b[k] == st_a[k], k
+            np.testing.assert_allclose(b[1][..., :3], a[1][..., :3], rtol=3e-5, atol=2e-5)
+            diff = np.abs(b[0].astype(int) - a[0].astype(int))
+            assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
 def test_render_multi_slab_resolve_on_one_device(rtw, ctx):
     """rtw_cuda_render_multi with a single context runs the same slab-resolve code path as N devices (one slab = the
     whole image, no peers): byte-identical to rtw_cuda_render, for widths that take the 4-pixel and the 1-pixel kernel."""

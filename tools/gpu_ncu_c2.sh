@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: gpu_ncu_c2.sh <tag> [ab-spec] [kernel regex]
-O=gpurun_out/r02
+O=${RTW_OUT:-gpurun_out/r02}
 mkdir -p $O
 SPEC=${2:-c2:1:3:1920x1080x64:1}
 K=${3:-k_megakernel_flat}
