@@ -1327,7 +1327,12 @@ static int accumulate_impl(rtw_ctx *ctx, const rtw_camera *cam, const rtw_render
         else if ((f & ~(uint32_t)FF_RECTS) == 0) pooled = 6;
     }
     // option RTW_BVH_KERNEL: 1 = per-lane state machine, 2 = per-warp ray queue in shared memory (k_megakernel_bvhq)
-    if (variant == VAR_BVH && pooled >= 1 && ctx->opt.num("RTW_BVH_KERNEL", 1) == 2) pooled = pooled == 4 ? 8 : 7;
+    // 3 = the state machine with speculative traversal (a lane postpones one leaf and goes on descending)
+    if (variant == VAR_BVH && pooled >= 1) {
+        const long bk = ctx->opt.num("RTW_BVH_KERNEL", 1);
+        if (bk == 2) pooled = pooled == 4 ? 8 : 7;
+        else if (bk == 3) pooled = pooled == 4 ? 10 : 9;
+    }
     const int per_sm = megakernel_ctas_per_sm(variant, stats, pooled, ctx->scene);
     if (per_sm <= 0) return fail(ctx, 2, "megakernel does not fit on an SM (flat image %u B)", ctx->scene.flat.total_f4 * 16u);
     const int grid = per_sm * ctx->n_sms;

@@ -3,7 +3,8 @@
 //   k_megakernel_flat<STATS,MINB,FEAT> K1 for scenes of <= 256 primitives (default): flat scan out of shared memory, second
 //                                    schedule (one Philox block + one evaluation of the sampling maps per iteration for the
 //                                    whole warp), specialised on the scene's features (FF_* in rtw_device.cuh)
-//   k_megakernel_bvh<STATS,FEAT>     K1 for larger scenes: BVH traversal as a per-lane state machine
+//   k_megakernel_bvh<STATS,FEAT,SPEC> K1 for larger scenes: BVH traversal as a per-lane state machine (SPEC: with one postponed
+//                                    leaf per lane, RTW_BVH_KERNEL=3, measured slower)
 //   k_megakernel_bvhq<STATS,FEAT,SLOTS,MINB> the same paths with a per-warp ray queue in shared memory (RTW_BVH_KERNEL=2; measured
 //                                    slower than the state machine, profiles/r02_l: kept for A/B measurements)
 //   k_megakernel_pooled<VARIANT,STATS> first flat schedule (RTW_FLAT_KERNEL=1, kept for A/B measurements)
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_megakernel_flat(const DevScene
 // new traversals start — all in one "service" phase that therefore runs reasonably full.
 // ---------------------------------------------------------------------------------------------
 
-template <bool STATS, uint32_t FEAT>
+template <bool STATS, uint32_t FEAT, bool SPEC = false>
 __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, const DevCamera cam, const DevRender rp) {
     Counters<STATS> cn;
     const uint32_t lane = threadIdx.x & 31;
@@ -388,13 +389,23 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
             const uint32_t m_leaf = __ballot_sync(0xffffffffu, trav && tv.at_leaf());
             const uint32_t m_int = __ballot_sync(0xffffffffu, trav && !tv.at_leaf());
             if (m_leaf && (__popc(m_leaf) >= (int)rp.leaf_threshold || m_int == 0u)) {
-                if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS, FEAT>(r, sc, stack, cn);
+                if constexpr (SPEC) {
+                    // SPEC: a lane parked at a leaf (m_leaf) has either nothing else to visit or a postponed leaf already; lanes
+                    // that are still descending bring their postponed leaf along (the phase runs anyway)
+                    if (trav && (tv.pend != 0u || tv.at_leaf())) trav = !tv.template spec_leaf_step<STATS, FEAT>(r, sc, stack, cn);
+                } else {
+                    if (trav && tv.at_leaf()) trav = !tv.template leaf_step<STATS, FEAT>(r, sc, stack, cn);
+                }
             }
         }
         // ---- interior phase ----
 #pragma unroll 1
         for (uint32_t k = 0; k < rp.steps_per_round; ++k) {
-            if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, stack, cn);
+            if constexpr (SPEC) {
+                if (trav && !tv.at_leaf()) trav = !tv.template spec_interior_step<STATS>(r, sc, stack, cn);
+            } else {
+                if (trav && !tv.at_leaf()) trav = !tv.template interior_step<STATS>(r, sc, stack, cn);
+            }
         }
     }
     if (STATS) cn.flush(rp.stats);
@@ -730,7 +741,9 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 // features (FF_SPHERES, FF_SPHERES | FF_TEX, FF_RECTS; event-counter builds always run the generic kernel)
 template <int VARIANT, bool STATS, int POOLED>
 static auto mega_kernel_ptr() {
-    if constexpr (POOLED == 8 && VARIANT == VAR_BVH) return k_megakernel_bvhq<STATS, FF_SPHERES, kBvhqSlots, 8>;  // ray-queue schedule
+    if constexpr (POOLED == 10 && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_SPHERES, true>;  // speculative schedule
+    else if constexpr (POOLED == 9 && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_ALL, true>;
+    else if constexpr (POOLED == 8 && VARIANT == VAR_BVH) return k_megakernel_bvhq<STATS, FF_SPHERES, kBvhqSlots, 8>;  // ray-queue schedule
     else if constexpr (POOLED == 7 && VARIANT == VAR_BVH) return k_megakernel_bvhq<STATS, FF_ALL, kBvhqSlots, 7>;
     else if constexpr (POOLED == 4 && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_SPHERES>;  // spheres, solid / checker textures
     else if constexpr (POOLED && VARIANT == VAR_BVH) return k_megakernel_bvh<STATS, FF_ALL>;
@@ -759,6 +772,7 @@ static cudaError_t launch_mega_t(const DevScene &sc, const DevCamera &cam, const
 // specialisation; event-counter builds run the generic kernel of the schedule
 static int bvh_pooled(int pooled, bool stats) {
     if (pooled == 7 || pooled == 8) return (pooled == 8 && !stats) ? 8 : 7;
+    if (pooled == 9 || pooled == 10) return (pooled == 10 && !stats) ? 10 : 9;
     return (pooled == 4 && !stats) ? 4 : 1;
 }
 
@@ -776,6 +790,7 @@ cudaError_t launch_megakernel(int variant, bool stats, int pooled, const DevScen
     RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
     RTW_CASE(VAR_BVH, false, 4); RTW_CASE(VAR_BVH, false, 7); RTW_CASE(VAR_BVH, true, 7); RTW_CASE(VAR_BVH, false, 8);
+    RTW_CASE(VAR_BVH, false, 9); RTW_CASE(VAR_BVH, true, 9); RTW_CASE(VAR_BVH, false, 10);
 #undef RTW_CASE
     return cudaErrorInvalidValue;
 }
@@ -797,6 +812,7 @@ int megakernel_ctas_per_sm(int variant, bool stats, int pooled, const DevScene &
     RTW_CASE(VAR_FLAT, false, 4); RTW_CASE(VAR_FLAT, false, 5); RTW_CASE(VAR_FLAT, false, 6);
     RTW_CASE(VAR_BVH, false, 0); RTW_CASE(VAR_BVH, true, 0); RTW_CASE(VAR_BVH, false, 1); RTW_CASE(VAR_BVH, true, 1);
     RTW_CASE(VAR_BVH, false, 4); RTW_CASE(VAR_BVH, false, 7); RTW_CASE(VAR_BVH, true, 7); RTW_CASE(VAR_BVH, false, 8);
+    RTW_CASE(VAR_BVH, false, 9); RTW_CASE(VAR_BVH, true, 9); RTW_CASE(VAR_BVH, false, 10);
 #undef RTW_CASE
     return 0;
 }

@@ -497,6 +497,7 @@ struct BvhTraversal {
     Hit h;
     uint32_t best_id;
     uint32_t cur;  // reference of the node to visit next
+    uint32_t pend; // speculative schedule only: a postponed leaf (0 = none; leaf references are never 0)
     int sp;
     // The stack itself is NOT a member: a dynamically indexed array inside the struct forces the whole struct into
     // local memory (ncu r01_m: four LDL and three STL per interior visit); as a separate array only the pushes and
@@ -511,6 +512,7 @@ struct BvhTraversal {
         h = Hit{__int_as_float(0x7f800000), kMiss};
         best_id = 0;
         sp = 0;
+        pend = 0u;
         if (sc.n_prims == 0) return true;
         cur = sc.nodes[0].a;
         return false;
@@ -546,11 +548,10 @@ struct BvhTraversal {
         return false;
     }
 
-    // one leaf visit (precondition: at_leaf()): the only primitive-test site.  Returns true when finished.
-    template <bool STATS, uint32_t FEAT = FF_ALL>
-    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
-                                              Counters<STATS> &cn) {
-        const uint32_t cnt = cur >> 28, at = cur & 0x0FFFFFFFu;
+    // the primitives of leaf reference `leaf`: the only primitive-test site
+    template <bool STATS, uint32_t FEAT>
+    __device__ __forceinline__ void test_leaf(uint32_t leaf, const Ray &r, const DevScene &sc, Counters<STATS> &cn) {
+        const uint32_t cnt = leaf >> 28, at = leaf & 0x0FFFFFFFu;
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint32_t slot = at + i;
             DevPrim p;
@@ -561,8 +562,48 @@ struct BvhTraversal {
                 if (t < h.t || h.slot == kMiss || id > best_id) { h.t = t; h.slot = slot; best_id = id; }
             }
         }
+    }
+
+    // one leaf visit (precondition: at_leaf()).  Returns true when finished.
+    template <bool STATS, uint32_t FEAT = FF_ALL>
+    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
+                                              Counters<STATS> &cn) {
+        test_leaf<STATS, FEAT>(cur, r, sc, cn);
         if (sp == 0) return true;
         cur = stack[--sp];
+        return false;
+    }
+
+    // ---- speculative schedule (Aila & Laine 2009, "speculative traversal"): a lane that reaches a leaf POSTPONES it (`pend`)
+    //      and goes on with the next stack entry instead of idling until enough lanes have a leaf to test.  The closest hit does
+    //      not depend on the order of the visits (the tie rule is symmetric); a postponed leaf only delays the shrinking of h.t,
+    //      i.e. a few node tests more.  Invariant: `cur` is always a node still to visit; pend != 0 is a second one (a leaf).
+    __device__ __forceinline__ void postpone(const uint32_t (&stack)[kBvhStack]) {
+        if (at_leaf() && pend == 0u && sp > 0) { pend = cur; cur = stack[--sp]; }
+    }
+    template <bool STATS>
+    __device__ __forceinline__ bool spec_interior_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
+                                                       Counters<STATS> &cn) {
+        if (interior_step<STATS>(r, sc, stack, cn)) {  // nothing left but the postponed leaf
+            if (pend == 0u) return true;
+            cur = pend; pend = 0u;
+            return false;
+        }
+        postpone(stack);
+        return false;
+    }
+    // precondition: pend != 0 || at_leaf()
+    template <bool STATS, uint32_t FEAT = FF_ALL>
+    __device__ __forceinline__ bool spec_leaf_step(const Ray &r, const DevScene &sc, uint32_t (&stack)[kBvhStack],
+                                                   Counters<STATS> &cn) {
+        const bool from_pend = pend != 0u;
+        test_leaf<STATS, FEAT>(from_pend ? pend : cur, r, sc, cn);
+        if (from_pend) pend = 0u;
+        else {
+            if (sp == 0) return true;
+            cur = stack[--sp];
+        }
+        postpone(stack);
         return false;
     }
 

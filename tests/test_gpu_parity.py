@@ -718,9 +718,10 @@ def test_wavefront_renders_the_same_paths_as_the_megakernel(rtw, ctx, knobs, sid
 
 
 @pytest.mark.parametrize("sid,grid,W,H,spp", [(1, 11, 203, 117, 9), (1, 3, 64, 40, 33), (2, 11, 97, 61, 5), (6, 11, 120, 120, 12), (4, 11, 80, 60, 8)])
-def test_bvh_ray_queue_schedule_renders_the_same_paths(rtw, ctx, sid, grid, W, H, spp):
-    """k_megakernel_bvhq (RTW_BVH_KERNEL=2: per-warp ray queue in shared memory, traversing lanes refilled from the ring) is
-    another schedule of the same paths as the per-lane state machine: identical Philox keys and closest hits => identical
+def test_bvh_schedules_render_the_same_paths(rtw, ctx, sid, grid, W, H, spp):
+    """k_megakernel_bvhq (RTW_BVH_KERNEL=2: per-warp ray queue in shared memory, traversing lanes refilled from the ring) and the
+    speculative state machine (RTW_BVH_KERNEL=3: a lane postpones one leaf and goes on descending) are
+    other schedules of the same paths as the per-lane state machine: identical Philox keys and closest hits => identical
     event counts and per-sample radiance; only the fp32 summation order per pixel differs.  Generic and spheres-only
     builds, ragged frames, threshold extremes (service phase at 1 and at 32 finished rays)."""
     hs = rtw.HostScene(sid, grid=grid)
@@ -731,15 +732,22 @@ def test_bvh_ray_queue_schedule_renders_the_same_paths(rtw, ctx, sid, grid, W, H
         p = ctx.params(W, H, 0, spp, spp, 50, bvh, flag, 42, hs.background)
         a = ctx.render(cam, p, want_accum=True)
         st_a = ctx.stats()
-        for opts in ({}, {"RTW_BVH_THRESH": "1", "RTW_BVH_LEAF": "1"}, {"RTW_BVH_THRESH": "32", "RTW_BVH_STEPS": "7"}):
-            with ctx.options(RTW_BVH_KERNEL="2", **opts):
+        for opts in ({"RTW_BVH_KERNEL": "2"}, {"RTW_BVH_KERNEL": "2", "RTW_BVH_THRESH": "1", "RTW_BVH_LEAF": "1"},
+                     {"RTW_BVH_KERNEL": "2", "RTW_BVH_THRESH": "32", "RTW_BVH_STEPS": "7"},
+                     {"RTW_BVH_KERNEL": "3"}, {"RTW_BVH_KERNEL": "3", "RTW_BVH_THRESH": "1", "RTW_BVH_LEAF": "1"},
+                     {"RTW_BVH_KERNEL": "3", "RTW_BVH_LEAF": "32", "RTW_BVH_STEPS": "7"}):
+            with ctx.options(**opts):
                 b = ctx.render(cam, p, want_accum=True)
                 st_b = ctx.stats()
             assert (b[1][..., 3] == spp).all()
             if flag:
                 assert st_b["paths"] == st_a["paths"] == W * H * spp and st_b["rays"] == st_a["rays"]
-                for k in ("scatter_diffuse", "scatter_metal", "scatter_dielectric", "emit_hits", "sphere_finalise", "node_tests"):
+                for k in ("scatter_diffuse", "scatter_metal", "scatter_dielectric", "emit_hits", "sphere_finalise"):
                     assert st_b[k] == st_a[k], k
+                if opts["RTW_BVH_KERNEL"] == "2":  # same visits in another order
+                    assert st_b["node_tests"] == st_a["node_tests"]
+                else:  # speculative traversal: a postponed leaf delays the shrinking of the search interval
+                    assert st_a["node_tests"] <= st_b["node_tests"] <= 1.5 * st_a["node_tests"]
             np.testing.assert_allclose(b[1][..., :3], a[1][..., :3], rtol=3e-5, atol=2e-5)
             diff = np.abs(b[0].astype(int) - a[0].astype(int))
             assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
