@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_megakernel_bvh(const DevScene sc, co
     uint32_t bounce = 0, cur_sample = 0, pixel = 0;
     bool alive = false, trav = false;
     BvhTraversal tv;
-    uint32_t stack[kBvhStack];
+    BvhStack stack;
     tv.sp = 0; tv.cur = 0;
     for (;;) {
         const uint32_t idle = __ballot_sync(0xffffffffu, !trav);
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_megakernel_bvhq(const DevScene
 
     Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
     BvhTraversal tv;
-    uint32_t stack[kBvhStack];
+    BvhStack stack;
     tv.sp = 0; tv.cur = 0;
     uint32_t my = 0;   // slot of the ray this lane is traversing
     bool trav = false, fin = false;  // fin: traversal finished, slot not yet pushed on `done`

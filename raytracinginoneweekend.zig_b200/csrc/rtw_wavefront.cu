@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend_bvh(WfState st, const De
     uint32_t slot = 0;
     Ray r{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
     BvhTraversal tv;
-    uint32_t stack[kBvhStack];
+    BvhStack stack;
     tv.sp = 0; tv.cur = 0;
     constexpr uint32_t kChunk = 32 * 8;
     for (;;) {
