@@ -97,7 +97,7 @@ void for_chunks(uint32_t n, unsigned max_threads, F &&fn) {
 // path); rtw_cuda_set_option changes one on a live context.
 const char *const kOptionNames[] = {"RTW_SPP_CHUNK", "RTW_BATCH_SPP", "RTW_BVH_LEAF", "RTW_BVH_THRESH", "RTW_BVH_STEPS", "RTW_WF_SLOTS",
                                     "RTW_BVH_LEAF_MAX", "RTW_BVH_BUILDER", "RTW_BUILD_THREADS", "RTW_UPLOAD_TRACE",
-                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES", "RTW_GROUP_ROUND", "RTW_BVH_KERNEL"};
+                                    "RTW_FLAT_KERNEL", "RTW_BOX_PRIMS", "RTW_FLAT_SPECIALISE", "RTW_MID_SPHERES", "RTW_GROUP_ROUND", "RTW_BVH_KERNEL", "RTW_LBVH_POW"};
 struct Options {
     std::map<std::string, std::string> v;
     const char *get(const char *name) const {
@@ -627,8 +627,16 @@ static int build_bvh_on_device(rtw_ctx *ctx, const std::vector<Box3d> &boxes, ui
     CK(cudaDeviceSynchronize());
     laps.lap("  lbvh alloc + H2D");
     LbvhInfo info;
+    // option RTW_LBVH_POW = p: Morton cells of axis a are (extent_a / widest extent)^-p times as long as the cubic grid's (p = 0:
+    // cubic); a thin axis then contributes its splits later
+    float axis_w[3] = {1.f, 1.f, 1.f};
+    if (const char *pw = ctx->opt.get("RTW_LBVH_POW")) {
+        const float p = (float)atof(pw), widest = std::max(sext[0], std::max(sext[1], sext[2]));
+        if (p > 0.f && widest > 0.f)
+            for (int a = 0; a < 3; ++a) axis_w[a] = std::pow(std::max(sext[a] / widest, 1e-6f), p);
+    }
     CK(build_lbvh(d_boxes.p, d_ids.p, ns, smn, sext, leaf_max, ctx->nodes.p, root_slot, pair_base, ctx->bvh_prim_id.p, nb,
-                  ctx->lbvh_arena.p, ctx->lbvh_arena.cap, ctx->stream, &info));
+                  ctx->lbvh_arena.p, ctx->lbvh_arena.cap, ctx->stream, &info, axis_w));
     laps.lap("  lbvh device build");
     const uint32_t total_depth = nb ? 1 + std::max(big.depth, info.depth) : info.depth;
     if (total_depth > 64) return 0;

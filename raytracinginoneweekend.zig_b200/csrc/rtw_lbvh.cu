@@ -259,7 +259,8 @@ size_t lbvh_arena_bytes(uint32_t ns) {
 
 cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns, const float cmin[3], const float cext[3],
                        uint32_t max_leaf, BvhNode *d_nodes, uint32_t root_slot, uint32_t pair_base, uint32_t *d_order,
-                       uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info) {
+                       uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info,
+                       const float *axis_weight) {
     if (ns < 2 || ns <= max_leaf || max_leaf < 1 || max_leaf > 15 || (pair_base & 1u)) return cudaErrorInvalidValue;
     cudaError_t e;
     ArenaLayout L;
@@ -284,6 +285,7 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     // the radix tree simply has no split there, instead of slicing a flat scene into overlapping slabs
     const float widest = fmaxf(cext[0], fmaxf(cext[1], cext[2]));
     g.sx = g.sy = g.sz = widest > 0.f ? 2097152.0f / widest : 0.f;
+    if (axis_weight) { g.sx *= axis_weight[0]; g.sy *= axis_weight[1]; g.sz *= axis_weight[2]; }  // <= 1: coarser cells on that axis
     const uint32_t tpb = 256, blocks = (ns + tpb - 1) / tpb;
     uint32_t root_info[2] = {0, 0};  // levels, pairs
     auto done = [&](cudaError_t err) { return err; };

@@ -27,7 +27,8 @@ struct LbvhInfo {
 size_t lbvh_arena_bytes(uint32_t ns);
 cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns, const float cmin[3], const float cext[3],
                        uint32_t max_leaf, BvhNode *d_nodes, uint32_t root_slot, uint32_t pair_base, uint32_t *d_order,
-                       uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info);
+                       uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info,
+                       const float *axis_weight = nullptr);  // per-axis factor (<= 1) on the cubic Morton grid's resolution
 
 // dst[k] = src[order[k]] for k < n (primitives into leaf order)
 cudaError_t gather_prims(const DevPrim *src, const uint32_t *d_order, DevPrim *dst, uint32_t n, cudaStream_t st);

@@ -1,6 +1,6 @@
 #!/bin/bash
 # final round-2 GPU call: parity suite, smoke, bench line (+ reference arm), per-config table, launch list
-O=gpurun_out/r02
+O=${RTW_OUT:-gpurun_out/r02}
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
 timeout 1800 python -m pytest tests -m gpu -q --timeout 900 > $O/pytest_gpu.log 2>&1; echo "pytest rc $?" >> $O/pytest_gpu.log
