@@ -260,7 +260,7 @@ size_t lbvh_arena_bytes(uint32_t ns) {
 cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns, const float cmin[3], const float cext[3],
                        uint32_t max_leaf, BvhNode *d_nodes, uint32_t root_slot, uint32_t pair_base, uint32_t *d_order,
                        uint32_t slot_base, void *d_arena, size_t arena_bytes, cudaStream_t st, LbvhInfo *info,
-                       const float *axis_weight) {
+                       const float *axis_weights, int n_candidates) {
     if (ns < 2 || ns <= max_leaf || max_leaf < 1 || max_leaf > 15 || (pair_base & 1u)) return cudaErrorInvalidValue;
     cudaError_t e;
     ArenaLayout L;
@@ -279,26 +279,45 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     void *tmp = arena + L.tmp;
     const size_t sort_bytes = L.sort_bytes;
 
-    Grid g;
-    g.mnx = cmin[0]; g.mny = cmin[1]; g.mnz = cmin[2];
     // one scale for the three axes (cubic cells): a thin axis then shares its leading bits across the whole scene and
-    // the radix tree simply has no split there, instead of slicing a flat scene into overlapping slabs
+    // the radix tree simply has no split there, instead of slicing a flat scene into overlapping slabs.  Candidate
+    // `axis_weights` (<= 1 per axis) make the cells of an axis longer still; the candidate whose tree has the smallest
+    // surface-area cost (k_fit sums it bottom-up: icost[0]) is the one that is emitted.
     const float widest = fmaxf(cext[0], fmaxf(cext[1], cext[2]));
-    g.sx = g.sy = g.sz = widest > 0.f ? 2097152.0f / widest : 0.f;
-    if (axis_weight) { g.sx *= axis_weight[0]; g.sy *= axis_weight[1]; g.sz *= axis_weight[2]; }  // <= 1: coarser cells on that axis
+    const float scale = widest > 0.f ? 2097152.0f / widest : 0.f;
     const uint32_t tpb = 256, blocks = (ns + tpb - 1) / tpb;
     uint32_t root_info[2] = {0, 0};  // levels, pairs
     auto done = [&](cudaError_t err) { return err; };
-
-    k_morton<<<blocks, tpb, 0, st>>>(d_boxes, d_ids, ns, g, keys0, vals0);
-    if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
-    size_t tb = sort_bytes;
-    if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, vals0, vals1, (int)ns, 0, 63, st)) != cudaSuccess) return done(e);
-    k_hierarchy<<<blocks, tpb, 0, st>>>(keys1, ns, range, gamma, pint, pleaf);
-    if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
-    if ((e = cudaMemsetAsync(arrivals, 0, 4 * n, st)) != cudaSuccess) return done(e);
-    k_fit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, max_leaf, range, gamma, pint, pleaf, arrivals, ibox, icost, surv);
-    if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
+    static const float kCubic[3] = {1.f, 1.f, 1.f};
+    if (n_candidates < 1 || !axis_weights) { axis_weights = kCubic; n_candidates = 1; }
+    auto fit = [&](const float *w) -> cudaError_t {  // Morton codes -> sort -> radix tree -> boxes, folding, costs
+        Grid g;
+        g.mnx = cmin[0]; g.mny = cmin[1]; g.mnz = cmin[2];
+        g.sx = scale * w[0]; g.sy = scale * w[1]; g.sz = scale * w[2];
+        k_morton<<<blocks, tpb, 0, st>>>(d_boxes, d_ids, ns, g, keys0, vals0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        size_t tb = sort_bytes;
+        if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, vals0, vals1, (int)ns, 0, 63, st)) != cudaSuccess) return e;
+        k_hierarchy<<<blocks, tpb, 0, st>>>(keys1, ns, range, gamma, pint, pleaf);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(arrivals, 0, 4 * n, st)) != cudaSuccess) return e;
+        k_fit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, max_leaf, range, gamma, pint, pleaf, arrivals, ibox, icost, surv);
+        return cudaGetLastError();
+    };
+    int best = 0;
+    float best_cost = 0.f;
+    if (n_candidates > 1) {
+        for (int c = 0; c < n_candidates; ++c) {
+            float cost = 0.f;
+            if ((e = fit(axis_weights + 3 * c)) != cudaSuccess) return done(e);
+            if ((e = cudaMemcpyAsync(&cost, icost, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(e);
+            if (info && c < LbvhInfo::kMaxCandidates) info->cost[c] = cost;
+            if (c == 0 || cost < best_cost) { best = c; best_cost = cost; }
+        }
+    }
+    if (n_candidates == 1 || best != n_candidates - 1)
+        if ((e = fit(axis_weights + 3 * best)) != cudaSuccess) return done(e);
     k_offsets<<<blocks, tpb, 0, st>>>(ns, range, gamma, pint, surv, ibox, pair);
     if ((e = cudaGetLastError()) != cudaSuccess) return done(e);
     k_emit<<<blocks, tpb, 0, st>>>(d_boxes, vals1, ns, range, gamma, surv, pair, ibox, d_nodes, root_slot, pair_base, d_order, slot_base);
@@ -307,6 +326,7 @@ cudaError_t build_lbvh(const float *d_boxes, const uint32_t *d_ids, uint32_t ns,
     if ((e = cudaMemcpyAsync(&root_info[1], reinterpret_cast<const char *>(ibox) + 28, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return done(e);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(e);
     if (info) {
+        info->chosen = best;
         info->n_nodes = pair_base + 2u * root_info[1];
         info->depth = root_info[0];
     }

@@ -171,6 +171,51 @@ def test_device_built_bvh_mixed_scene(rtw, oracle, ctx, knobs, seed):
     assert np.array_equal(acc_l, acc_s)
 
 
+def test_device_built_bvh_picks_the_morton_grid_by_surface_area_cost(rtw, oracle, ctx):
+    """The device builder fits one radix tree per candidate Morton grid (cells of a thin axis 1x, (1/thin)x, (1/thin)^2x,
+    (1/thin)^4x as long as the cubic grid's) and emits the one with the smallest surface-area cost.  On a sheet of spheres
+    (config C4's generator: 9*10^4 spheres on the curved ground) that is not the cubic grid, and the rays need fewer node
+    tests; the hits are the same whichever grid made the tree, and equal to the oracle's."""
+    hs = rtw.HostScene(rtw.host_lib.SCENE_SPHERE_FIELD, grid=150)
+    osc = oracle.OracleScene.from_desc(hs.desc, keep=hs)
+    cam = hs.camera(aspect=1.5)
+    rng = np.random.default_rng(23)
+    n = 20000
+    rays = np.zeros((n, 7))
+    rays[:, 0:3] = rng.uniform(-120, 120, (n, 3)) * [1, 0.05, 1] + [0, 8, 0]
+    rays[:, 3:6] = rng.normal(size=(n, 3)) * [1, 0.3, 1]
+    rays[:, 6] = rng.uniform(0, 1, n)
+    oid, ot, _, _ = osc.trace_rays(rays, 32, use_bvh=True)
+    p = ctx.params(192, 128, 0, 4, 4, 50, rtw.abi.VARIANT_MEGA_BVH, rtw.abi.FLAG_COUNT_EVENTS, 42, hs.background)
+    tests_per_ray = {}
+    for label, opts in (("auto", {}), ("cubic", {"RTW_LBVH_POW": "0"}), ("p2", {"RTW_LBVH_POW": "2"})):
+        with ctx.options(RTW_BVH_BUILDER="lbvh", **opts):
+            ctx.upload_scene(hs.desc, keep=hs)
+            assert ctx.stats()["bvh_builder"] == rtw.abi.BVH_BUILDER_LBVH and ctx.stats()["bvh_depth"] <= 64
+            gid, gt, _, _ = ctx.trace_rays(rays, 32, rtw.abi.VARIANT_MEGA_BVH)
+            assert np.array_equal(gid, oid) and np.array_equal(gt, ot)
+            ctx.render(cam, p)
+            st = ctx.stats()
+            tests_per_ray[label] = st["node_tests"] / st["rays"]
+    # 9.76 against 10.00 here (the sheet is only 22 units high over 300 x 300); 46.9 against 51.7 on the 10^6-sphere config
+    assert tests_per_ray["auto"] < 0.985 * tests_per_ray["cubic"], tests_per_ray
+    assert tests_per_ray["auto"] <= 1.02 * tests_per_ray["p2"], tests_per_ray
+    # a scene that fills its bounds: the extents are alike, the cubic grid is the only candidate (same tree as RTW_LBVH_POW=0)
+    b = scene_util.DescBuilder()
+    m = b.diffuse(b.solid((0.5, 0.5, 0.5)))
+    for c in rng.uniform(-20, 20, (3000, 3)):
+        b.sphere(tuple(c), 0.3, m)
+    desc = b.build()
+    rays2 = scene_util.random_rays(rng, 8000, extent=25.0)
+    got = []
+    for opts in ({}, {"RTW_LBVH_POW": "0"}):
+        with ctx.options(RTW_BVH_BUILDER="lbvh", **opts):
+            ctx.upload_scene(desc, keep=desc)
+            got.append((ctx.stats()["bvh_nodes"], ctx.trace_rays(rays2, 0, rtw.abi.VARIANT_MEGA_BVH)))
+    assert got[0][0] == got[1][0]
+    assert np.array_equal(got[0][1][0], got[1][1][0]) and np.array_equal(got[0][1][1], got[1][1][1])
+
+
 def test_device_built_bvh_coincident_centroids(rtw, oracle, ctx, knobs):
     """Equal Morton keys (stacks of concentric spheres): the radix tree splits ties by position and stays shallow."""
     knobs.setenv("RTW_BVH_BUILDER", "lbvh")
