@@ -486,21 +486,15 @@ __device__ __forceinline__ bool slab(const BvhNode &n, const Ray &r, float idx, 
 
 constexpr int kBvhStack = 64;
 
-// The traversal stack: node references and, with RTW_BVH_TSTACK, the entry distance the node's box had when it was pushed.  A
-// popped node is visited unconditionally otherwise — one fetch and two slab tests that all fail when a hit found in the
-// meantime lies in front of the box; with the distance kept, a stale entry is dropped by the pop itself (same hits bit for bit:
-// the comparison is the slab test's own against the current closest hit, and a child's computed t_near is never below its
-// parent's).  MEASURED AND OFF (profiles/r02_m): with the ordered descent only 1.6-3 % of the node tests are stale (485 spheres
-// 24.81 -> 24.05 per ray, 10^6 spheres 51.68 -> 50.86) while every push and pop moves two words of local memory instead of
-// one: 485 spheres +0.7 %, 10^6 spheres +10 % time.
-#ifndef RTW_BVH_TSTACK
-#define RTW_BVH_TSTACK 0
-#endif
+// The traversal stack: node references in local memory (the entries of one depth form a 128-byte line per warp).
+// Measured and removed (profiles/r02_m): entry distances kept on the stack so that stale entries are dropped by the pop (only
+// 1.6-3 % of the node tests are stale with the ordered descent; the second word per entry cost 10 % on the 10^6-sphere scene),
+// and the first 16 / 24 entries in shared memory, one bank per lane (+3 % on 485 spheres, +10 % on 10^6: the address
+// arithmetic and the L1 capacity given to the carve-out cost more than the local-memory lines did).
 struct BvhStack {
     uint32_t ref[kBvhStack];
-#if RTW_BVH_TSTACK
-    float tn[kBvhStack];
-#endif
+    __device__ __forceinline__ void put(int at, uint32_t v) { ref[at] = v; }
+    __device__ __forceinline__ uint32_t get(int at) const { return ref[at]; }
 };
 
 // stack entry / node reference: index in the low 28 bits, leaf primitive count in the top 4.  The builders store
@@ -538,8 +532,8 @@ struct BvhTraversal {
     __device__ __forceinline__ bool at_leaf() const { return (cur >> 28) != 0u; }
 
     // one interior visit: both children of `cur` (precondition: !at_leaf()).  Returns true when finished.
-    template <bool STATS>
-    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, BvhStack &stack,
+    template <bool STATS, class Stack>
+    __device__ __forceinline__ bool interior_step(const Ray &r, const DevScene &sc, Stack &stack,
                                                   Counters<STATS> &cn) {
         const float4 *q = reinterpret_cast<const float4 *>(sc.nodes + cur);
         float4 l0, l1, r0, r1;
@@ -554,11 +548,7 @@ struct BvhTraversal {
         const uint32_t el = L.a, er = R.a;
         if (hl && hr) {
             const bool left_first = tl <= tr;
-            stack.ref[sp] = left_first ? er : el;  // depth is bounded by the builder (<= kBvhStack)
-#if RTW_BVH_TSTACK
-            stack.tn[sp] = left_first ? tr : tl;
-#endif
-            ++sp;
+            stack.put(sp++, left_first ? er : el);  // depth is bounded by the builder (<= kBvhStack)
             cur = left_first ? el : er;
         } else if (hl || hr) {
             cur = hl ? el : er;
@@ -569,19 +559,11 @@ struct BvhTraversal {
     }
 
     // next node to visit from the stack; false when there is none (the traversal is finished)
-    __device__ __forceinline__ bool pop(BvhStack &stack) {
-#if RTW_BVH_TSTACK
-        const float reach = h.t * 1.0000004f;  // slab()'s acceptance, against the closest hit as it is NOW
-        while (sp > 0) {
-            --sp;
-            if (stack.tn[sp] <= reach) { cur = stack.ref[sp]; return true; }
-        }
-        return false;
-#else
+    template <class Stack>
+    __device__ __forceinline__ bool pop(Stack &stack) {
         if (sp == 0) return false;
-        cur = stack.ref[--sp];
+        cur = stack.get(--sp);
         return true;
-#endif
     }
 
     // the primitives of leaf reference `leaf`: the only primitive-test site
@@ -601,8 +583,8 @@ struct BvhTraversal {
     }
 
     // one leaf visit (precondition: at_leaf()).  Returns true when finished.
-    template <bool STATS, uint32_t FEAT = FF_ALL>
-    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, BvhStack &stack,
+    template <bool STATS, uint32_t FEAT = FF_ALL, class Stack>
+    __device__ __forceinline__ bool leaf_step(const Ray &r, const DevScene &sc, Stack &stack,
                                               Counters<STATS> &cn) {
         test_leaf<STATS, FEAT>(cur, r, sc, cn);
         return !pop(stack);
@@ -612,15 +594,16 @@ struct BvhTraversal {
     //      and goes on with the next stack entry instead of idling until enough lanes have a leaf to test.  The closest hit does
     //      not depend on the order of the visits (the tie rule is symmetric); a postponed leaf only delays the shrinking of h.t,
     //      i.e. a few node tests more.  Invariant: `cur` is always a node still to visit; pend != 0 is a second one (a leaf).
-    __device__ __forceinline__ void postpone(BvhStack &stack) {
+    template <class Stack>
+    __device__ __forceinline__ void postpone(Stack &stack) {
         if (at_leaf() && pend == 0u && sp > 0) {
             const uint32_t leaf = cur;
             if (pop(stack)) pend = leaf;  // nothing else worth a visit: stay parked at the leaf
             else cur = leaf;
         }
     }
-    template <bool STATS>
-    __device__ __forceinline__ bool spec_interior_step(const Ray &r, const DevScene &sc, BvhStack &stack,
+    template <bool STATS, class Stack>
+    __device__ __forceinline__ bool spec_interior_step(const Ray &r, const DevScene &sc, Stack &stack,
                                                        Counters<STATS> &cn) {
         if (interior_step<STATS>(r, sc, stack, cn)) {  // nothing left but the postponed leaf
             if (pend == 0u) return true;
@@ -631,8 +614,8 @@ struct BvhTraversal {
         return false;
     }
     // precondition: pend != 0 || at_leaf()
-    template <bool STATS, uint32_t FEAT = FF_ALL>
-    __device__ __forceinline__ bool spec_leaf_step(const Ray &r, const DevScene &sc, BvhStack &stack,
+    template <bool STATS, uint32_t FEAT = FF_ALL, class Stack>
+    __device__ __forceinline__ bool spec_leaf_step(const Ray &r, const DevScene &sc, Stack &stack,
                                                    Counters<STATS> &cn) {
         const bool from_pend = pend != 0u;
         test_leaf<STATS, FEAT>(from_pend ? pend : cur, r, sc, cn);
@@ -643,8 +626,8 @@ struct BvhTraversal {
     }
 
     // at most one interior visit followed by at most one leaf visit.  Returns true when finished.
-    template <bool STATS>
-    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, BvhStack &stack, Counters<STATS> &cn) {
+    template <bool STATS, class Stack>
+    __device__ __forceinline__ bool step(const Ray &r, const DevScene &sc, Stack &stack, Counters<STATS> &cn) {
         if (!at_leaf() && interior_step<STATS>(r, sc, stack, cn)) return true;
         if (at_leaf()) return leaf_step<STATS>(r, sc, stack, cn);
         return false;
