@@ -828,11 +828,28 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
             if (!lower(i)) return fail(ctx, 1, "too many distinct instance chains on spheres (max 4095)");
     laps.lap("lower to fp32");
 
+    // which primitive / texture kinds the scene has: selects the specialised megakernels (FF_* in rtw_device.cuh)
+    {
+        uint32_t feat = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtw_prim &p = s->prims[i];
+            const bool sphere = p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE;
+            feat |= sphere ? FF_SPHERES : FF_RECTS;
+            if (sphere && p.xform >= 0) feat |= FF_TEX;  // instanced sphere: uv in object space (finalise_hit)
+        }
+        for (uint32_t i = 0; i < s->n_textures; ++i)
+            if (s->textures[i].kind != RTW_TEX_SOLID && s->textures[i].kind != RTW_TEX_CHECKER) feat |= FF_TEX;
+        ctx->flat_feat = feat;
+    }
+
     // ---- BVH ------------------------------------------------------------------------------------------
     // Small and medium scenes: binned SAH on the host (best trees, microseconds to milliseconds).  Large scenes:
     // Morton/Karras build on the device (rtw_lbvh.cu), with the few primitives that dwarf the rest (the ground
     // sphere) kept out of the Morton order and grafted next to the root as their own host-built subtree.
-    uint32_t leaf_max = 4;
+    // Leaves of up to four primitives where the surface-area heuristic prefers them — for scenes with rects and boxes (Cornell:
+    // leaves of one primitive +2 % time); sphere-only scenes get one sphere per leaf (10^6 spheres -0.8 %, 485 spheres -1.6 %,
+    // 9*10^4 spheres -1.9 %: a leaf's sphere test costs more than the node test a fold saves)
+    uint32_t leaf_max = (ctx->flat_feat & FF_RECTS) ? 4 : 1;
     leaf_max = (uint32_t)std::max(1l, std::min(15l, ctx->opt.num("RTW_BVH_LEAF_MAX", leaf_max)));  // 4-bit count in node refs
     CK(ctx->prims_flat.upload(flat));
     const auto t_bvh = std::chrono::steady_clock::now();
@@ -858,19 +875,6 @@ int rtw_cuda_upload_scene(rtw_ctx *ctx, const rtw_scene_desc *s) {
     ctx->stats.ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_bvh).count();
     ctx->stats.bvh_builder = bvh_on_device ? RTW_BVH_BUILDER_LBVH : RTW_BVH_BUILDER_SAH;
 
-    // which primitive / texture kinds the scene has: selects the specialised megakernels (FF_* in rtw_device.cuh)
-    {
-        uint32_t feat = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const rtw_prim &p = s->prims[i];
-            const bool sphere = p.kind == RTW_PRIM_SPHERE || p.kind == RTW_PRIM_MOVING_SPHERE;
-            feat |= sphere ? FF_SPHERES : FF_RECTS;
-            if (sphere && p.xform >= 0) feat |= FF_TEX;  // instanced sphere: uv in object space (finalise_hit)
-        }
-        for (uint32_t i = 0; i < s->n_textures; ++i)
-            if (s->textures[i].kind != RTW_TEX_SOLID && s->textures[i].kind != RTW_TEX_CHECKER) feat |= FF_TEX;
-        ctx->flat_feat = feat;
-    }
     // ---- shared-memory image for the flat scan: segmented by kind, small spheres in groups of four --------
     FlatLayout fl{};
     std::vector<float4> blob;
